@@ -1,0 +1,336 @@
+/*
+ * pddm.h -- C ABI of libpddm_b200.so: the sm_100a (B200) kernels under the improved-diffusion hot path of
+ * ArturPrzybysz/ProbabilisticDeepDiffusionModels.
+ *
+ * The reference has no FFI of its own (it is pure Python on stock torch ops); each entry point
+ * below names the reference call site (file:line under /root/reference) whose arithmetic it replaces.  The
+ * Python host (probabilisticdeepdiffusionmodels_b200/_lib.py) binds these with ctypes and registers them as
+ * torch.library ops; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless its name ends in _host.
+ *   - the caller owns all memory (incl. workspaces); the library never allocates device memory and keeps no
+ *     pointer after returning.  Every call only enqueues work on `stream` (no sync, CUDA-graph capturable).
+ *   - return value: 0 on success, a negative pddm_status otherwise; nothing throws across the ABI.
+ *   - activations inside the network are NHWC ("channels last") bf16 or fp32; the model boundary is NCHW fp32.
+ *   - timesteps are 1-indexed (tables are read at [t-1]) exactly like the reference.
+ */
+#ifndef PDDM_H_
+#define PDDM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* pddm_stream_t; /* cudaStream_t */
+
+enum pddm_status {
+  PDDM_OK = 0,
+  PDDM_ERR_BAD_ARG = -1,     /* null pointer, non-positive size, misaligned pointer */
+  PDDM_ERR_UNSUPPORTED = -2, /* shape outside what the kernel supports (see each op) */
+  PDDM_ERR_WORKSPACE = -3,   /* workspace_bytes smaller than pddm_*_workspace() */
+  PDDM_ERR_CUDA = -4,        /* launch failed (cudaPeekAtLastError) */
+  PDDM_ERR_ARCH = -5,        /* device is not sm_100 (no fallback path exists) */
+  PDDM_ERR_TMA = -6          /* cuTensorMapEncodeTiled rejected the descriptor */
+};
+
+enum pddm_dtype { PDDM_F32 = 0, PDDM_BF16 = 1 };
+
+int pddm_version(void);
+const char* pddm_strerror(int status);
+/* 0 if the current device can run the library (compute capability 10.x), PDDM_ERR_ARCH otherwise. */
+int pddm_check_device(void);
+int pddm_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Diffusion math (fp32, NCHW, HBM-bound elementwise kernels)
+ * ---------------------------------------------------------------------------------------------------- */
+
+/* q_sample: x_t = sqrt_ab[t-1]*x0 + sqrt_1mab[t-1]*noise.  Replaces Engine.q_mean_std/get_q_t
+ * (src/engine.py:251-261).  t: int64[B] (device) or NULL -> t_const for every sample. */
+typedef struct {
+  const float* x0;
+  const float* noise;
+  float* x_t;
+  const int64_t* t;
+  int32_t t_const;
+  const float* alphas_hat_sqrt;         /* [T] */
+  const float* one_min_alphas_hat_sqrt; /* [T] */
+  int32_t B;
+  int32_t chw; /* elements per sample */
+} pddm_q_sample_params;
+int pddm_q_sample(const pddm_q_sample_params* p, pddm_stream_t stream);
+
+/* per-sample mean squared error  L_b = mean_chw (noise - pred)^2  (+ optional gradient).
+ * Replaces get_loss / mean_flat (src/engine.py:263-277, src/utils.py:13-17).
+ * pred may be the first `C` channels of a [B, c_total, HW] tensor (learned-variance models): pred_c_total,
+ * c = channels compared, hw = pixels.  If grad_pred != NULL it receives
+ *   grad_pred[b, c, :] = gscale[b] * 2 * (pred - noise) / (c*hw)   for c < C  (channels >= C untouched). */
+typedef struct {
+  const float* pred;
+  const float* noise;
+  float* per_sample; /* [B] or NULL */
+  float* grad_pred;  /* same layout as pred, or NULL */
+  const float* gscale; /* [B] upstream dL/dL_b, needed iff grad_pred */
+  int32_t B, C, c_total, hw;
+} pddm_sq_err_params;
+int pddm_sq_err(const pddm_sq_err_params* p, pddm_stream_t stream);
+
+/* The 12 coefficient tables of Engine.__init__ (src/engine.py:121-150), device-resident fp32 [T]. */
+typedef struct {
+  const float* betas;
+  const float* alphas_sqrt;
+  const float* posterior_variance;
+  const float* sqrt_recip_alphas_cumprod;
+  const float* sqrt_recipm1_alphas_cumprod;
+  const float* posterior_mean_coef1;
+  const float* posterior_mean_coef2;
+  const float* denoising_coef;
+  const float* alphas_hat_sqrt;
+  const float* one_min_alphas_hat_sqrt;
+  const float* posterior_log_variance_clipped; /* log(cat(pv[1:2], pv[1:]))   */
+  const float* log_betas;
+  int32_t T;
+} pddm_tables;
+
+/* One reverse step x_{t-1} = mean(x_t, eps) - sigma * z.  Replaces model_mean_from_epsilon /
+ * xstart_from_epsilon / q_posterior / get_sigma / denoising_step (src/engine.py:354-397, 477-490).
+ *   model_out: [B, c_out, HW] with c_out = C (eps) or 2C (eps | v, learned variance)
+ *   z: noise or NULL (mean only); z is ignored at t == 1 (src/engine.py:389-394)
+ *   t_step_dev: if non-NULL the step index is read from device memory (CUDA-graph replay), else t_step
+ *   clip: clamp the x0 estimate to [-1,1] and go through the posterior mean (src/engine.py:366-367)
+ *   sigma_mode: 0 = sqrt(beta), 1 = sqrt(beta_tilde), 2 = learned (needs c_out == 2C) */
+typedef struct {
+  const float* x_t;
+  const float* model_out;
+  const float* z;
+  float* x_prev;
+  pddm_tables tab;
+  const int32_t* t_step_dev;
+  int32_t t_step;
+  int32_t B, C, c_out, hw;
+  int32_t clip, sigma_mode;
+} pddm_p_sample_params;
+int pddm_p_sample_step(const pddm_p_sample_params* p, pddm_stream_t stream);
+
+/* Chain bookkeeping for graph replay: t_dev[0] -= 1; t_vec[b] = (float)t_dev[0] for all b. */
+int pddm_step_advance(int32_t* t_dev, float* t_vec, int32_t B, pddm_stream_t stream);
+
+/* Variational-bound terms in bits/dim per sample.  Replaces normal_kl / discretized_gaussian_log_likelihood
+ * (src/utils.py:50-115) and the drivers _calculate_L_T/_L_intermediate/_L_0 (src/engine.py:437-506).
+ *   mode 0 (fixed variance, reference NLL eval): out[b] = t==1 ? -dll(x0; mean, log sigma)/ln2
+ *                                                            : KL(q_post || N(mean, sigma^2))/ln2
+ *          with mean = no-clip model mean (src/engine.py:375-381) and sigma per sigma_mode (0/1)
+ *   mode 1 (learned variance, App. C.5): model_out = [eps | v]; mean through x0-estimate without clip;
+ *          if grad_v != NULL also writes d out[b] / d v  ([B, C, HW])
+ *   mode 2 (prior term L_T, src/engine.py:437-444): out[b] = KL(q(x_T|x0) || N(0,1))/ln2, uses x0 only. */
+typedef struct {
+  const float* x0;
+  const float* x_t;
+  const float* model_out;
+  const int64_t* t; /* [B] */
+  float* out;       /* [B] */
+  float* grad_v;    /* mode 1 only, may be NULL */
+  pddm_tables tab;
+  int32_t B, C, c_out, hw;
+  int32_t mode, sigma_mode;
+} pddm_vlb_params;
+int pddm_vlb_terms(const pddm_vlb_params* p, pddm_stream_t stream);
+
+/* timestep_embedding (src/modules/nn.py:104-122): out[b] = [cos(t*f) | sin(t*f) | 0-pad], f_i = exp(-ln(max_period)*i/half).
+ * t is int64 (t_is_float = 0) or float32 (sampling passes float timesteps, src/engine.py:386). */
+int pddm_timestep_embedding(const void* t, int32_t t_is_float, void* out, int32_t out_dtype, int32_t B, int32_t dim,
+                            float max_period, pddm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Layout / elementwise helpers (NHWC activations)
+ * ---------------------------------------------------------------------------------------------------- */
+/* [B,C,HW] fp32 -> [B,HW,C] (dst dtype) and back. */
+int pddm_nchw_to_nhwc(const float* src, void* dst, int32_t dst_dtype, int32_t B, int32_t C, int32_t HW,
+                      pddm_stream_t stream);
+int pddm_nhwc_to_nchw(const void* src, int32_t src_dtype, float* dst, int32_t B, int32_t C, int32_t HW,
+                      pddm_stream_t stream);
+/* dst[m, dst_off + c] = src[m, src_off + c] for c < C ; rows have ld_src / ld_dst elements (bf16). th.cat
+ * (src/modules/unet.py:492) and its backward are expressed with this. */
+int pddm_copy_channels(const void* src, int32_t ld_src, int32_t src_off, void* dst, int32_t ld_dst, int32_t dst_off,
+                       int64_t M, int32_t C, pddm_stream_t stream);
+/* nearest x2 upsample (src/modules/unet.py:79) of NHWC bf16 and its adjoint (2x2 sum). */
+int pddm_upsample2x(const void* src, void* dst, int32_t B, int32_t H, int32_t W, int32_t C, pddm_stream_t stream);
+int pddm_upsample2x_bwd(const void* grad_dst, void* grad_src, int32_t B, int32_t H, int32_t W, int32_t C,
+                        pddm_stream_t stream);
+/* Stride-2 phase split: dst[p, b, i, j, :] = src[b, 2i + (p>>1), 2j + (p&1), :]  (H, W even) and its inverse.
+ * Lets the stride-2 Downsample conv (src/modules/unet.py:102) run as a tap-GEMM on unit-stride TMA boxes. */
+int pddm_phase_split(const void* src, void* dst, int32_t B, int32_t H, int32_t W, int32_t C, pddm_stream_t stream);
+int pddm_phase_merge(const void* src, void* dst, int32_t B, int32_t H, int32_t W, int32_t C, pddm_stream_t stream);
+/* y = a + b (bf16, n elements; n % 8 == 0): gradient fan-in. */
+int pddm_add_bf16(const void* a, const void* b, void* y, int64_t n, pddm_stream_t stream);
+/* SiLU on an fp32 vector -> out dtype; and its backward (dx = dy * silu'(x)).  (src/modules/nn.py:13-15) */
+int pddm_silu(const float* x, void* y, int32_t y_dtype, int64_t n, pddm_stream_t stream);
+int pddm_silu_bwd(const float* x, const float* dy, float* dx, int64_t n, pddm_stream_t stream);
+/* out[c] (+)= sum_m x[m, c]  (x bf16 [M, ld], fp32 out [C]); used for conv bias gradients. */
+int pddm_colsum(const void* x, int32_t ld, int64_t M, int32_t C, float* out, int32_t accumulate, pddm_stream_t stream);
+/* out[b, c] = sum_{hw} x[b, hw, c] : per-sample column sums (gradient of the broadcast emb add). */
+int pddm_colsum_per_sample(const void* x, int32_t B, int32_t HW, int32_t C, float* out, pddm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * GroupNorm(32 groups, eps) [+ per-sample scale/shift] [+ SiLU]   (src/modules/nn.py:13-20,94-101;
+ * ResBlock order src/modules/unet.py:188-200).  x: [B, HW, C] bf16 or fp32, y: bf16.
+ *   z = gn(x)*gamma + beta ; if scale_shift: z = z*(1+scale[b,c]) + shift[b,c] ; y = silu ? z*sigmoid(z) : z
+ * mean/rstd [B, G] fp32 are saved for the backward.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* x;
+  int32_t x_dtype;
+  const float* gamma;
+  const float* beta;
+  const float* scale; /* [B, ld_ss] or NULL */
+  const float* shift; /* [B, ld_ss] or NULL */
+  int32_t ld_ss;
+  void* y; /* bf16 [B, HW, C] */
+  float* mean;
+  float* rstd;
+  int32_t B, HW, C, G;
+  float eps;
+  int32_t silu;
+} pddm_gn_fwd_params;
+int pddm_gn_silu_fwd(const pddm_gn_fwd_params* p, pddm_stream_t stream);
+
+/* Backward.  dy: bf16 [B,HW,C].  Outputs: dx (dx_dtype), dgamma/dbeta [C] fp32 (overwritten),
+ * dx_colsum [B, C] fp32 or NULL (= sum_hw dx: gradient of a per-sample broadcast add in front of the norm,
+ * i.e. of `h + emb_out` src/modules/unet.py:199 and of the producing conv's bias),
+ * dscale/dshift [B, ld_ss] or NULL.  workspace: pddm_gn_silu_bwd_workspace(B, C) bytes. */
+typedef struct {
+  const void* x;
+  int32_t x_dtype;
+  const void* dy;
+  const float* gamma;
+  const float* beta;
+  const float* scale;
+  const float* shift;
+  int32_t ld_ss;
+  const float* mean;
+  const float* rstd;
+  void* dx;
+  int32_t dx_dtype;
+  float* dgamma;
+  float* dbeta;
+  float* dx_colsum;
+  float* dscale;
+  float* dshift;
+  int32_t B, HW, C, G;
+  int32_t silu;
+} pddm_gn_bwd_params;
+size_t pddm_gn_silu_bwd_workspace(int32_t B, int32_t C);
+int pddm_gn_silu_bwd(const pddm_gn_bwd_params* p, void* workspace, size_t workspace_bytes, pddm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Convolution / linear as a tcgen05 "tap GEMM"   (conv_nd / linear, src/modules/nn.py:23-40; call sites
+ * src/modules/unet.py:70,102,149,163,174,219,221,342,344,153)
+ *
+ *   y[b, oh, ow, n] = bias[n] + bcast[b, n] + residual[b, oh, ow, n]
+ *                     + sum_{tap} sum_{c} x[b + tap_db, h + tap_dh, w + tap_dw, c] * w[n, tap, c]
+ *   with (oh, ow) = (h*out_sh + out_oh, w*out_sw + out_ow) and (b, h, w) ranging over [B, H, W].
+ *
+ * x is a 4-D NHWC bf16 tensor [x_NB, H, W, ldx] (ldx >= Cin: channel-slice views allowed, ldx % 8 == 0); reads
+ * outside [0,H)x[0,W) are zero (TMA out-of-bounds fill) which implements padding=1.  w is bf16
+ * [Cout, ntaps*Cin] (tap-major, channel-minor rows).  3x3/s1: 9 taps (dh,dw in -1..1); 1x1 and linear: 1 tap;
+ * stride-2: taps over the phase-split input (tap_db = phase*B); dgrad: the same kernel on the flipped/transposed
+ * weight pack.  Cin % 32 == 0, Cout % 8 == 0.  Accumulation is fp32 in tensor memory.
+ * ---------------------------------------------------------------------------------------------------- */
+#define PDDM_MAX_TAPS 9
+typedef struct {
+  const void* x;
+  const void* w;
+  const float* bias;     /* [Cout] or NULL */
+  const float* bcast;    /* [B, ld_bcast] or NULL */
+  const void* residual;  /* [B, out_H, out_W, Cout] or NULL */
+  void* y;               /* [B, out_H, out_W, Cout] */
+  int32_t ld_bcast;
+  int32_t res_dtype, y_dtype;
+  int32_t x_NB, B, H, W, Cin, ldx, Cout;
+  int32_t ntaps;
+  int32_t tap_db[PDDM_MAX_TAPS], tap_dh[PDDM_MAX_TAPS], tap_dw[PDDM_MAX_TAPS];
+  int32_t out_H, out_W, out_sh, out_sw, out_oh, out_ow;
+} pddm_conv_params;
+int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream);
+
+/* Weight gradient:  dw[n, tap, c] = sum_{b,h,w} dy[b, h, w, n] * x[b + tap_db, h + tap_dh, w + tap_dw, c]
+ * (dy indexed in the conv's tile space [B, H, W]; for strided outputs pass the phase view).  Split-K partial
+ * sums go to the workspace and are reduced deterministically into dw_out, fp32, laid out either packed
+ * [Cout, ntaps, Cin] (layout 0) or as the parameter [Cout, Cin, ntaps] (layout 1 = torch Conv2d weight). */
+typedef struct {
+  const void* x;
+  const void* dy;
+  float* dw;
+  int32_t x_NB, B, H, W, Cin, ldx, Cout, lddy;
+  int32_t ntaps;
+  int32_t tap_db[PDDM_MAX_TAPS], tap_dh[PDDM_MAX_TAPS], tap_dw[PDDM_MAX_TAPS];
+  int32_t dw_layout;
+  int32_t accumulate; /* dw += instead of dw = */
+} pddm_wgrad_params;
+size_t pddm_conv2d_wgrad_workspace(const pddm_wgrad_params* p);
+int pddm_conv2d_wgrad(const pddm_wgrad_params* p, void* workspace, size_t workspace_bytes, pddm_stream_t stream);
+
+/* fp32 parameter [Cout, Cin, kh*kw] -> bf16 GEMM operand.
+ *   mode 0 (forward): dst[n, tap, c]            = w[n, c, tap]
+ *   mode 1 (dgrad):   dst[c, ntaps-1-tap, n]    = w[n, c, tap]   (flipped taps, transposed channels) */
+int pddm_pack_conv_weight(const float* w, void* dst, int32_t Cout, int32_t Cin, int32_t ntaps, int32_t mode,
+                          pddm_stream_t stream);
+
+/* Thin convolutions on CUDA cores (too narrow for a UMMA tile): the stem conv Cin<=4 reading the NCHW fp32 model
+ * input (src/modules/unet.py:353) and the head conv Cout<=8 writing the NCHW fp32 model output
+ * (src/modules/unet.py:440), with their gradients. */
+int pddm_stem_conv_fwd(const float* x_nchw, const float* w, const float* bias, void* y_nhwc_bf16, int32_t B, int32_t Cin,
+                       int32_t H, int32_t W, int32_t Cout, pddm_stream_t stream);
+int pddm_stem_conv_wgrad(const float* x_nchw, const void* dy_nhwc_bf16, float* dw, float* dbias, int32_t B, int32_t Cin,
+                         int32_t H, int32_t W, int32_t Cout, pddm_stream_t stream);
+int pddm_head_conv_fwd(const void* x_nhwc_bf16, const float* w, const float* bias, float* y_nchw, int32_t B, int32_t Cin,
+                       int32_t H, int32_t W, int32_t Cout, pddm_stream_t stream);
+int pddm_head_conv_bwd(const void* x_nhwc_bf16, const float* w, const float* dy_nchw, void* dx_nhwc_bf16, float* dw,
+                       float* dbias, int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t Cout, pddm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * QKVAttention (src/modules/unet.py:237-256): per (sample, head), softmax_fp32((q*s)(k*s)^T) v, s = d^-1/4.
+ * qkv: bf16 [B, T, 3*heads*d] with the reference's head-major [q|k|v] channel packing; out: bf16 [B, T, heads*d].
+ * lse [B, heads, T] fp32 is saved for the backward.  d in {32, 64, 96, 128}, T <= 256.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* qkv;
+  void* out;
+  float* lse;
+  int32_t B, T, heads, d;
+} pddm_attn_fwd_params;
+int pddm_attn_fwd(const pddm_attn_fwd_params* p, pddm_stream_t stream);
+typedef struct {
+  const void* qkv;
+  const void* out;
+  const void* dout;
+  const float* lse;
+  void* dqkv; /* bf16 [B, T, 3*heads*d] */
+  int32_t B, T, heads, d;
+} pddm_attn_bwd_params;
+int pddm_attn_bwd(const pddm_attn_bwd_params* p, pddm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Fused Adam (+ EMA) over a flat fp32 parameter arena (torch.optim.Adam defaults, src/engine.py:238-248;
+ * Ema.update src/modules/ema.py:21-33).  ema may be NULL.  step is the 1-based step count.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  float* ema;
+  int64_t n;
+  float lr, beta1, beta2, eps, weight_decay, ema_decay, grad_scale;
+  int32_t step;
+} pddm_adam_params;
+int pddm_adam_ema_step(const pddm_adam_params* p, pddm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDDM_H_ */

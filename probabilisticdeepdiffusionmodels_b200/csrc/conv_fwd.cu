@@ -1,0 +1,347 @@
+// Tap-GEMM convolution / linear forward (and data gradient) on tcgen05 tensor cores.
+//
+//   D[m, n] = sum_tap sum_c  X[pixel(m) + offset(tap), c] * Wp[n, tap, c]        (fp32 accumulate in TMEM)
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer: per K-block one 4-D box load of the (shifted) NHWC activation tile -- out-of-bounds
+//               coordinates are zero-filled by the TMA unit, which is the conv's padding -- and one 2-D box load of the
+//               packed weight tile; both land in 128B/64B-swizzled K-major shared memory.
+//   warp 1      single-thread tcgen05.mma issuer (UMMA 128 x BLOCK_N x 16, bf16 -> fp32), accumulators double-buffered
+//               in tensor memory so the epilogue of tile i overlaps the main loop of tile i+1.
+//   warp 2      TMEM allocator.
+//   warps 4..7  epilogue: tcgen05.ld 32 lanes x 32 columns, + bias + per-sample broadcast (timestep embedding)
+//               + residual, convert, 128-bit stores.
+// Pipelines: smem full/empty mbarrier ring (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue).
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace pddm {
+
+struct ConvKArgs {
+  const float* bias;
+  const float* bcast;
+  const void* residual;
+  void* y;
+  int ld_bcast, res_dtype, y_dtype;
+  int B, H, W, Cout;
+  int BW, BH, BB, tiles_w, tiles_h, m_tiles, n_tiles;
+  int block_n, bk, kblocks_per_tap, ntaps;
+  int tap_db[PDDM_MAX_TAPS], tap_dh[PDDM_MAX_TAPS], tap_dw[PDDM_MAX_TAPS];
+  int out_H, out_W, out_sh, out_sw, out_oh, out_ow;
+  int stages, a_slot_bytes, a_tx_bytes, b_bytes;
+  uint32_t idesc, layout_type, sbo_bytes, tmem_cols;
+};
+
+constexpr int kConvThreads = 256;
+constexpr int kMaxStages = 8;
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ ConvKArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = a.a_slot_bytes + a.b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.stages * stage_bytes);
+  uint64_t* full_bar = bars;                      // [stages]
+  uint64_t* empty_bar = bars + kMaxStages;        // [stages]
+  uint64_t* tmem_full = bars + 2 * kMaxStages;    // [2]
+  uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = a.m_tiles * a.n_tiles;
+  const int total_kb = a.ntaps * a.kblocks_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr, a.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_tile = tile % a.m_tiles, n_tile = tile / a.m_tiles;
+        const int tw = m_tile % a.tiles_w;
+        const int th = (m_tile / a.tiles_w) % a.tiles_h;
+        const int tb = m_tile / (a.tiles_w * a.tiles_h);
+        const int b0 = tb * a.BB, h0 = th * a.BH, w0 = tw * a.BW;
+        for (int tap = 0; tap < a.ntaps; ++tap) {
+          const int cb = b0 + a.tap_db[tap], ch = h0 + a.tap_dh[tap], cw = w0 + a.tap_dw[tap];
+          for (int kc = 0; kc < a.kblocks_per_tap; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], a.a_tx_bytes + a.b_bytes);
+            uint8_t* sa = smem + stage * stage_bytes;
+            tma_load_4d(sa, &tmA, &full_bar[stage], kc * a.bk, cw, ch, cb);
+            tma_load_2d(sa + a.a_slot_bytes, &tmB, &full_bar[stage], (tap * a.kblocks_per_tap + kc) * a.bk,
+                        n_tile * a.block_n);
+            if (++stage == a.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * a.block_n;
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          const uint32_t sb = sa + a.a_slot_bytes;
+          const uint64_t adesc = make_smem_desc(sa, 16, a.sbo_bytes, a.layout_type);
+          const uint64_t bdesc = make_smem_desc(sb, 16, a.sbo_bytes, a.layout_type);
+          const int ksteps = a.bk >> 4;
+          for (int k = 0; k < ksteps; ++k) {
+            // advance 16 elements (32 B) along K inside the swizzled row: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, a.idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == a.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int rows_per_b = a.BW * a.BH;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_tile = tile % a.m_tiles, n_tile = tile / a.m_tiles;
+      const int tw = m_tile % a.tiles_w;
+      const int th = (m_tile / a.tiles_w) % a.tiles_h;
+      const int tb = m_tile / (a.tiles_w * a.tiles_h);
+      const int bb = row / rows_per_b;
+      const int rr = row - bb * rows_per_b;
+      const int hh = rr / a.BW;
+      const int ww = rr - hh * a.BW;
+      const int b = tb * a.BB + bb, h = th * a.BH + hh, w = tw * a.BW + ww;
+      const bool valid = (bb < a.BB) && (b < a.B) && (h < a.H) && (w < a.W);
+      const size_t opix = (static_cast<size_t>(b) * a.out_H + (h * a.out_sh + a.out_oh)) * a.out_W +
+                          (w * a.out_sw + a.out_ow);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * a.block_n;
+      const int nchunks = a.block_n >> 5;
+      for (int c = 0; c < nchunks; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        const int n0 = n_tile * a.block_n + c * 32;
+        if (valid && n0 < a.Cout) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int n = n0 + g * 8;
+            if (n < a.Cout) {
+              if (a.bias) {
+                const float4 b0v = __ldg(reinterpret_cast<const float4*>(a.bias + n));
+                const float4 b1v = __ldg(reinterpret_cast<const float4*>(a.bias + n + 4));
+                v[g * 8 + 0] += b0v.x; v[g * 8 + 1] += b0v.y; v[g * 8 + 2] += b0v.z; v[g * 8 + 3] += b0v.w;
+                v[g * 8 + 4] += b1v.x; v[g * 8 + 5] += b1v.y; v[g * 8 + 6] += b1v.z; v[g * 8 + 7] += b1v.w;
+              }
+              if (a.bcast) {
+                const float* bp = a.bcast + static_cast<size_t>(b) * a.ld_bcast + n;
+                const float4 b0v = __ldg(reinterpret_cast<const float4*>(bp));
+                const float4 b1v = __ldg(reinterpret_cast<const float4*>(bp + 4));
+                v[g * 8 + 0] += b0v.x; v[g * 8 + 1] += b0v.y; v[g * 8 + 2] += b0v.z; v[g * 8 + 3] += b0v.w;
+                v[g * 8 + 4] += b1v.x; v[g * 8 + 5] += b1v.y; v[g * 8 + 6] += b1v.z; v[g * 8 + 7] += b1v.w;
+              }
+              if (a.residual) {
+                if (a.res_dtype == PDDM_BF16) {
+                  const uint4 rv = __ldg(reinterpret_cast<const uint4*>(
+                      reinterpret_cast<const __nv_bfloat16*>(a.residual) + opix * a.Cout + n));
+                  const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
+                    v[g * 8 + 2 * j] += __low2float(h2);
+                    v[g * 8 + 2 * j + 1] += __high2float(h2);
+                  }
+                } else {
+                  const float* rp = reinterpret_cast<const float*>(a.residual) + opix * a.Cout + n;
+                  const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));
+                  const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + 4));
+                  v[g * 8 + 0] += r0.x; v[g * 8 + 1] += r0.y; v[g * 8 + 2] += r0.z; v[g * 8 + 3] += r0.w;
+                  v[g * 8 + 4] += r1.x; v[g * 8 + 5] += r1.y; v[g * 8 + 6] += r1.z; v[g * 8 + 7] += r1.w;
+                }
+              }
+              if (a.y_dtype == PDDM_BF16) {
+                uint4 o;
+                o.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
+                o.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+                o.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
+                o.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.y) + opix * a.Cout + n) = o;
+              } else {
+                float* yp = reinterpret_cast<float*>(a.y) + opix * a.Cout + n;
+                *reinterpret_cast<float4*>(yp) = make_float4(v[g * 8 + 0], v[g * 8 + 1], v[g * 8 + 2], v[g * 8 + 3]);
+                *reinterpret_cast<float4*>(yp + 4) =
+                    make_float4(v[g * 8 + 4], v[g * 8 + 5], v[g * 8 + 6], v[g * 8 + 7]);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, a.tmem_cols);
+  }
+}
+
+static int pick_block_n(int cout) {
+  const int c32 = (cout + 31) / 32 * 32;
+  if (c32 <= 256) return c32;
+  int best = 256, best_pad = 1 << 30;
+  const int cands[3] = {256, 192, 128};
+  for (int i = 0; i < 3; ++i) {
+    const int pad = (cout + cands[i] - 1) / cands[i] * cands[i];
+    if (pad < best_pad) {
+      best_pad = pad;
+      best = cands[i];
+    }
+  }
+  return best;
+}
+
+}  // namespace pddm
+
+using namespace pddm;
+
+extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!p || !p->x || !p->w || !p->y) return PDDM_ERR_BAD_ARG;
+  if (!device_info().ok) return PDDM_ERR_ARCH;
+  if (p->B <= 0 || p->H <= 0 || p->W <= 0 || p->Cin <= 0 || p->Cout <= 0 || p->ntaps <= 0 ||
+      p->ntaps > PDDM_MAX_TAPS || p->x_NB < p->B)
+    return PDDM_ERR_BAD_ARG;
+  if (p->Cin % 32 != 0 || p->Cout % 8 != 0 || p->ldx % 8 != 0 || p->ldx < p->Cin) return PDDM_ERR_UNSUPPORTED;
+  if (!aligned16(p->x) || !aligned16(p->w) || !aligned16(p->y) || (p->residual && !aligned16(p->residual)) ||
+      (p->bias && !aligned16(p->bias)) || (p->bcast && (!aligned16(p->bcast) || p->ld_bcast % 4 != 0)))
+    return PDDM_ERR_BAD_ARG;
+
+  ConvKArgs a;
+  a.bias = p->bias;
+  a.bcast = p->bcast;
+  a.residual = p->residual;
+  a.y = p->y;
+  a.ld_bcast = p->ld_bcast;
+  a.res_dtype = p->res_dtype;
+  a.y_dtype = p->y_dtype;
+  a.B = p->B; a.H = p->H; a.W = p->W; a.Cout = p->Cout;
+  a.BW = p->W < 128 ? p->W : 128;
+  a.BH = 128 / a.BW < p->H ? 128 / a.BW : p->H;
+  if (a.BH < 1) a.BH = 1;
+  a.BB = 128 / (a.BW * a.BH) < p->B ? 128 / (a.BW * a.BH) : p->B;
+  if (a.BB < 1) a.BB = 1;
+  a.tiles_w = (p->W + a.BW - 1) / a.BW;
+  a.tiles_h = (p->H + a.BH - 1) / a.BH;
+  const int tiles_b = (p->B + a.BB - 1) / a.BB;
+  a.m_tiles = a.tiles_w * a.tiles_h * tiles_b;
+  a.block_n = pick_block_n(p->Cout);
+  a.n_tiles = (p->Cout + a.block_n - 1) / a.block_n;
+  a.bk = (p->Cin % 64 == 0) ? 64 : 32;
+  a.kblocks_per_tap = p->Cin / a.bk;
+  a.ntaps = p->ntaps;
+  for (int i = 0; i < PDDM_MAX_TAPS; ++i) {
+    a.tap_db[i] = i < p->ntaps ? p->tap_db[i] : 0;
+    a.tap_dh[i] = i < p->ntaps ? p->tap_dh[i] : 0;
+    a.tap_dw[i] = i < p->ntaps ? p->tap_dw[i] : 0;
+  }
+  a.out_H = p->out_H; a.out_W = p->out_W; a.out_sh = p->out_sh; a.out_sw = p->out_sw;
+  a.out_oh = p->out_oh; a.out_ow = p->out_ow;
+  const int swz = a.bk * 2;  // 128 or 64 bytes per K-major row
+  a.layout_type = swz == 128 ? kLayoutSW128 : kLayoutSW64;
+  a.sbo_bytes = 8 * swz;
+  a.a_slot_bytes = 128 * swz;
+  a.a_tx_bytes = a.BW * a.BH * a.BB * swz;
+  a.b_bytes = a.block_n * swz;
+  a.idesc = make_idesc_bf16(128, a.block_n, 0, 0);
+  uint32_t cols = 32;
+  while (cols < static_cast<uint32_t>(2 * a.block_n)) cols <<= 1;
+  a.tmem_cols = cols;
+  const int stage_bytes = a.a_slot_bytes + a.b_bytes;
+  const int budget = device_info().max_smem_optin - 1024 - 512;
+  int stages = budget / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return PDDM_ERR_UNSUPPORTED;
+  a.stages = stages;
+  const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 + 512;
+
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[4] = {static_cast<uint64_t>(p->Cin), static_cast<uint64_t>(p->W), static_cast<uint64_t>(p->H),
+                              static_cast<uint64_t>(p->x_NB)};
+    const uint64_t str[3] = {static_cast<uint64_t>(p->ldx) * 2, static_cast<uint64_t>(p->W) * p->ldx * 2,
+                             static_cast<uint64_t>(p->H) * p->W * p->ldx * 2};
+    const uint32_t box[4] = {static_cast<uint32_t>(a.bk), static_cast<uint32_t>(a.BW), static_cast<uint32_t>(a.BH),
+                             static_cast<uint32_t>(a.BB)};
+    int rc = make_tmap_bf16(&tmA, p->x, 4, dims, str, box, swz);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t ktot = static_cast<uint64_t>(p->ntaps) * p->Cin;
+    const uint64_t dims[2] = {ktot, static_cast<uint64_t>(p->Cout)};
+    const uint64_t str[1] = {ktot * 2};
+    const uint32_t box[2] = {static_cast<uint32_t>(a.bk), static_cast<uint32_t>(a.block_n)};
+    int rc = make_tmap_bf16(&tmB, p->w, 2, dims, str, box, swz);
+    if (rc) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             device_info().max_smem_optin) != cudaSuccess)
+      return PDDM_ERR_CUDA;
+    attr_set = true;
+  }
+  const int total_tiles = a.m_tiles * a.n_tiles;
+  const int grid = total_tiles < device_info().sm_count ? total_tiles : device_info().sm_count;
+  conv_fwd_kernel<<<grid, kConvThreads, smem_bytes, stream>>>(tmA, tmB, a);
+  return launch_status();
+}

@@ -1,0 +1,92 @@
+#include "host_common.h"
+
+#include <mutex>
+
+namespace pddm {
+
+const DeviceInfo& device_info() {
+  // Per-process, per-current-device cache (one process per GPU is the deployment model).
+  static DeviceInfo info[64];
+  static bool have[64] = {false};
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+    static DeviceInfo bad = {0, 0, 0};
+    return bad;
+  }
+  std::lock_guard<std::mutex> lock(mu);
+  if (!have[dev]) {
+    cudaDeviceProp prop;
+    DeviceInfo d = {0, 0, 0};
+    if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) {
+      d.ok = (prop.major == 10);
+      d.sm_count = prop.multiProcessorCount;
+      d.max_smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+    }
+    info[dev] = d;
+    have[dev] = true;
+  }
+  return info[dev];
+}
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+  });
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, int swizzle_bytes) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return PDDM_ERR_TMA;
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bdim[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i + 1 < rank) gstr[i] = strides_bytes[i];
+  }
+  CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
+                  gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? PDDM_OK : PDDM_ERR_TMA;
+}
+
+}  // namespace pddm
+
+extern "C" {
+
+int pddm_version(void) { return 100; }
+
+const char* pddm_strerror(int status) {
+  switch (status) {
+    case PDDM_OK: return "ok";
+    case PDDM_ERR_BAD_ARG: return "bad argument (null/misaligned pointer or non-positive size)";
+    case PDDM_ERR_UNSUPPORTED: return "shape not supported by the sm_100a kernel";
+    case PDDM_ERR_WORKSPACE: return "workspace too small";
+    case PDDM_ERR_CUDA: return "CUDA launch error";
+    case PDDM_ERR_ARCH: return "device is not sm_100 (B200); this library has no fallback path";
+    case PDDM_ERR_TMA: return "cuTensorMapEncodeTiled failed";
+    default: return "unknown pddm status";
+  }
+}
+
+int pddm_check_device(void) { return pddm::device_info().ok ? PDDM_OK : PDDM_ERR_ARCH; }
+int pddm_sm_count(void) { return pddm::device_info().sm_count; }
+
+}  // extern "C"
