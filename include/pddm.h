@@ -167,6 +167,8 @@ int pddm_phase_split(const void* src, void* dst, int32_t B, int32_t H, int32_t W
 int pddm_phase_merge(const void* src, void* dst, int32_t B, int32_t H, int32_t W, int32_t C, pddm_stream_t stream);
 /* y = a + b (bf16, n elements; n % 8 == 0): gradient fan-in. */
 int pddm_add_bf16(const void* a, const void* b, void* y, int64_t n, pddm_stream_t stream);
+/* elementwise dtype conversion fp32 <-> bf16 (n elements). */
+int pddm_convert(const void* x, int32_t x_dtype, void* y, int32_t y_dtype, int64_t n, pddm_stream_t stream);
 /* SiLU on an fp32 vector -> out dtype; and its backward (dx = dy * silu'(x)).  (src/modules/nn.py:13-15) */
 int pddm_silu(const float* x, void* y, int32_t y_dtype, int64_t n, pddm_stream_t stream);
 int pddm_silu_bwd(const float* x, const float* dy, float* dx, int64_t n, pddm_stream_t stream);
@@ -196,7 +198,8 @@ typedef struct {
   float eps;
   int32_t silu;
 } pddm_gn_fwd_params;
-int pddm_gn_silu_fwd(const pddm_gn_fwd_params* p, pddm_stream_t stream);
+size_t pddm_gn_silu_fwd_workspace(int32_t B, int32_t G);
+int pddm_gn_silu_fwd(const pddm_gn_fwd_params* p, void* workspace, size_t workspace_bytes, pddm_stream_t stream);
 
 /* Backward.  dy: bf16 [B,HW,C].  Outputs: dx (dx_dtype), dgamma/dbeta [C] fp32 (overwritten),
  * dx_colsum [B, C] fp32 or NULL (= sum_hw dx: gradient of a per-sample broadcast add in front of the norm,
@@ -236,7 +239,8 @@ int pddm_gn_silu_bwd(const pddm_gn_bwd_params* p, void* workspace, size_t worksp
  *
  * x is a 4-D NHWC bf16 tensor [x_NB, H, W, ldx] (ldx >= Cin: channel-slice views allowed, ldx % 8 == 0); reads
  * outside [0,H)x[0,W) are zero (TMA out-of-bounds fill) which implements padding=1.  w is bf16
- * [Cout, ntaps*Cin] (tap-major, channel-minor rows).  3x3/s1: 9 taps (dh,dw in -1..1); 1x1 and linear: 1 tap;
+ * [Cout, w_ntaps*Cin] (tap-major, channel-minor rows); tap i multiplies weight slot tap_w[i] (a stride-2 data
+ * gradient uses a subset of the 9 slots per output phase).  3x3/s1: 9 taps (dh,dw in -1..1); 1x1 and linear: 1 tap;
  * stride-2: taps over the phase-split input (tap_db = phase*B); dgrad: the same kernel on the flipped/transposed
  * weight pack.  Cin % 32 == 0, Cout % 8 == 0.  Accumulation is fp32 in tensor memory.
  * ---------------------------------------------------------------------------------------------------- */
@@ -253,6 +257,8 @@ typedef struct {
   int32_t x_NB, B, H, W, Cin, ldx, Cout;
   int32_t ntaps;
   int32_t tap_db[PDDM_MAX_TAPS], tap_dh[PDDM_MAX_TAPS], tap_dw[PDDM_MAX_TAPS];
+  int32_t tap_w[PDDM_MAX_TAPS]; /* weight slot read by each tap: w[n, tap_w[tap], c]; w has w_ntaps slots per row */
+  int32_t w_ntaps;
   int32_t out_H, out_W, out_sh, out_sw, out_oh, out_ow;
 } pddm_conv_params;
 int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream);
@@ -327,8 +333,12 @@ typedef struct {
   int64_t n;
   float lr, beta1, beta2, eps, weight_decay, ema_decay, grad_scale;
   int32_t step;
+  const int32_t* step_dev; /* if non-NULL the step count is read from device memory (CUDA-graph replay) */
+  const float* lr_dev;     /* if non-NULL overrides lr (LR schedulers under graph replay) */
 } pddm_adam_params;
 int pddm_adam_ema_step(const pddm_adam_params* p, pddm_stream_t stream);
+/* *counter += delta (single thread); advances device-side step counters between graph replays. */
+int pddm_counter_add(int32_t* counter, int32_t delta, pddm_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,7 @@ struct ConvKArgs {
   int B, H, W, Cout;
   int BW, BH, BB, tiles_w, tiles_h, m_tiles, n_tiles;
   int block_n, bk, kblocks_per_tap, ntaps;
-  int tap_db[PDDM_MAX_TAPS], tap_dh[PDDM_MAX_TAPS], tap_dw[PDDM_MAX_TAPS];
+  int tap_db[PDDM_MAX_TAPS], tap_dh[PDDM_MAX_TAPS], tap_dw[PDDM_MAX_TAPS], tap_w[PDDM_MAX_TAPS];
   int out_H, out_W, out_sh, out_sw, out_oh, out_ow;
   int stages, a_slot_bytes, a_tx_bytes, b_bytes;
   uint32_t idesc, layout_type, sbo_bytes, tmem_cols;
@@ -91,7 +91,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             mbar_expect_tx(&full_bar[stage], a.a_tx_bytes + a.b_bytes);
             uint8_t* sa = smem + stage * stage_bytes;
             tma_load_4d(sa, &tmA, &full_bar[stage], kc * a.bk, cw, ch, cb);
-            tma_load_2d(sa + a.a_slot_bytes, &tmB, &full_bar[stage], (tap * a.kblocks_per_tap + kc) * a.bk,
+            tma_load_2d(sa + a.a_slot_bytes, &tmB, &full_bar[stage], (a.tap_w[tap] * a.kblocks_per_tap + kc) * a.bk,
                         n_tile * a.block_n);
             if (++stage == a.stages) {
               stage = 0;
@@ -259,7 +259,7 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
   if (!p || !p->x || !p->w || !p->y) return PDDM_ERR_BAD_ARG;
   if (!device_info().ok) return PDDM_ERR_ARCH;
   if (p->B <= 0 || p->H <= 0 || p->W <= 0 || p->Cin <= 0 || p->Cout <= 0 || p->ntaps <= 0 ||
-      p->ntaps > PDDM_MAX_TAPS || p->x_NB < p->B)
+      p->ntaps > PDDM_MAX_TAPS || p->x_NB < p->B || p->w_ntaps < 1 || p->w_ntaps > PDDM_MAX_TAPS)
     return PDDM_ERR_BAD_ARG;
   if (p->Cin % 32 != 0 || p->Cout % 8 != 0 || p->ldx % 8 != 0 || p->ldx < p->Cin) return PDDM_ERR_UNSUPPORTED;
   if (!aligned16(p->x) || !aligned16(p->w) || !aligned16(p->y) || (p->residual && !aligned16(p->residual)) ||
@@ -293,6 +293,8 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
     a.tap_db[i] = i < p->ntaps ? p->tap_db[i] : 0;
     a.tap_dh[i] = i < p->ntaps ? p->tap_dh[i] : 0;
     a.tap_dw[i] = i < p->ntaps ? p->tap_dw[i] : 0;
+    a.tap_w[i] = i < p->ntaps ? p->tap_w[i] : 0;
+    if (i < p->ntaps && (p->tap_w[i] < 0 || p->tap_w[i] >= p->w_ntaps)) return PDDM_ERR_BAD_ARG;
   }
   a.out_H = p->out_H; a.out_W = p->out_W; a.out_sh = p->out_sh; a.out_sw = p->out_sw;
   a.out_oh = p->out_oh; a.out_ow = p->out_ow;
@@ -326,7 +328,7 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
     if (rc) return rc;
   }
   {
-    const uint64_t ktot = static_cast<uint64_t>(p->ntaps) * p->Cin;
+    const uint64_t ktot = static_cast<uint64_t>(p->w_ntaps) * p->Cin;
     const uint64_t dims[2] = {ktot, static_cast<uint64_t>(p->Cout)};
     const uint64_t str[1] = {ktot * 2};
     const uint32_t box[2] = {static_cast<uint32_t>(a.bk), static_cast<uint32_t>(a.block_n)};

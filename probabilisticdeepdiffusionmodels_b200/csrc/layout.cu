@@ -1,0 +1,654 @@
+// Layout and elementwise helpers around the NHWC bf16 activation format, plus the two "thin" convolutions
+// (3-channel stem, 3/6-channel head) that are too narrow for a UMMA tile and run on CUDA cores.
+// All of these are HBM/L2-bound: 128-bit accesses, channel-contiguous thread mapping.
+#include <cuda_bf16.h>
+
+#include "host_common.h"
+
+namespace pddm {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __low2float(h[i]);
+    f[2 * i + 1] = __high2float(h[i]);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 v;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+
+static int grid_for(long long items, int threads) {
+  long long b = (items + threads - 1) / threads;
+  const long long cap = static_cast<long long>(device_info().sm_count > 0 ? device_info().sm_count : 148) * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+#define GRID_STRIDE(i, n)                                                                        \
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < (n);     \
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+
+// ---------------------------------------------------------------------------------- NCHW <-> NHWC
+template <typename TOut>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, TOut* __restrict__ dst, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* s = src + static_cast<size_t>(b) * C * HW;
+  TOut* d = dst + static_cast<size_t>(b) * C * HW;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? s[static_cast<size_t>(c) * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    if (p < HW && c < C) d[static_cast<size_t>(p) * C + c] = static_cast<TOut>(tile[threadIdx.x][i]);
+  }
+}
+template <typename TIn>
+__global__ void nhwc_to_nchw_kernel(const TIn* __restrict__ src, float* __restrict__ dst, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const TIn* s = src + static_cast<size_t>(b) * C * HW;
+  float* d = dst + static_cast<size_t>(b) * C * HW;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? static_cast<float>(s[static_cast<size_t>(p) * C + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    if (p < HW && c < C) d[static_cast<size_t>(c) * HW + p] = tile[threadIdx.x][i];
+  }
+}
+
+// ---------------------------------------------------------------------------------- channel copy / add
+__global__ void copy_channels_kernel(const bf16* __restrict__ src, int ld_src, bf16* __restrict__ dst, int ld_dst,
+                                     long long M, int C8) {
+  const long long n = M * C8;
+  GRID_STRIDE(i, n) {
+    const long long m = i / C8;
+    const int c = static_cast<int>(i - m * C8) * 8;
+    *reinterpret_cast<uint4*>(dst + m * ld_dst + c) = *reinterpret_cast<const uint4*>(src + m * ld_src + c);
+  }
+}
+__global__ void add_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ y,
+                                long long n8) {
+  GRID_STRIDE(i, n8) {
+    float fa[8], fb[8];
+    unpack8(a[i], fa);
+    unpack8(b[i], fb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) fa[j] += fb[j];
+    y[i] = pack8(fa);
+  }
+}
+
+// ---------------------------------------------------------------------------------- upsample / phases
+__global__ void upsample2x_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int B, int H, int W, int C8) {
+  const long long n = static_cast<long long>(B) * 2 * H * 2 * W * C8;
+  GRID_STRIDE(i, n) {
+    const int c = static_cast<int>(i % C8);
+    long long r = i / C8;
+    const int x = static_cast<int>(r % (2 * W)); r /= 2 * W;
+    const int y = static_cast<int>(r % (2 * H));
+    const int b = static_cast<int>(r / (2 * H));
+    reinterpret_cast<uint4*>(dst)[i] =
+        reinterpret_cast<const uint4*>(src)[((static_cast<long long>(b) * H + (y >> 1)) * W + (x >> 1)) * C8 + c];
+  }
+}
+__global__ void upsample2x_bwd_kernel(const bf16* __restrict__ gd, bf16* __restrict__ gs, int B, int H, int W,
+                                      int C8) {
+  const long long n = static_cast<long long>(B) * H * W * C8;
+  GRID_STRIDE(i, n) {
+    const int c = static_cast<int>(i % C8);
+    long long r = i / C8;
+    const int x = static_cast<int>(r % W); r /= W;
+    const int y = static_cast<int>(r % H);
+    const int b = static_cast<int>(r / H);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        float f[8];
+        unpack8(reinterpret_cast<const uint4*>(
+                    gd)[((static_cast<long long>(b) * 2 * H + 2 * y + dy) * 2 * W + 2 * x + dx) * C8 + c], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
+    reinterpret_cast<uint4*>(gs)[i] = pack8(acc);
+  }
+}
+// split: dst[p][b][i][j] = src[b][2i + (p>>1)][2j + (p&1)] ; merge is the inverse (iterate over the full-res side)
+template <bool SPLIT>
+__global__ void phase_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int B, int H, int W, int C8) {
+  const int H2 = H / 2, W2 = W / 2;
+  const long long n = static_cast<long long>(B) * H * W * C8;
+  GRID_STRIDE(i, n) {  // i indexes the full-resolution tensor
+    const int c = static_cast<int>(i % C8);
+    long long r = i / C8;
+    const int x = static_cast<int>(r % W); r /= W;
+    const int y = static_cast<int>(r % H);
+    const int b = static_cast<int>(r / H);
+    const int p = ((y & 1) << 1) | (x & 1);
+    const long long j = (((static_cast<long long>(p) * B + b) * H2 + (y >> 1)) * W2 + (x >> 1)) * C8 + c;
+    if (SPLIT) reinterpret_cast<uint4*>(dst)[j] = reinterpret_cast<const uint4*>(src)[i];
+    else reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[j];
+  }
+}
+
+// ---------------------------------------------------------------------------------- SiLU on vectors
+__global__ void silu_kernel(const float* __restrict__ x, void* __restrict__ y, int y_dtype, long long n) {
+  GRID_STRIDE(i, n) {
+    const float v = x[i];
+    const float s = v / (1.f + expf(-v));
+    if (y_dtype == PDDM_BF16) static_cast<bf16*>(y)[i] = __float2bfloat16(s);
+    else static_cast<float*>(y)[i] = s;
+  }
+}
+__global__ void silu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx,
+                                long long n) {
+  GRID_STRIDE(i, n) {
+    const float v = x[i];
+    const float sg = 1.f / (1.f + expf(-v));
+    dx[i] = dy[i] * sg * (1.f + v * (1.f - sg));
+  }
+}
+
+// ---------------------------------------------------------------------------------- dtype conversion
+template <typename TI, typename TO>
+__global__ void convert_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long n) {
+  GRID_STRIDE(i, n) y[i] = static_cast<TO>(static_cast<float>(x[i]));
+}
+
+// ---------------------------------------------------------------------------------- column sums
+// blockDim = (C8 vectors, rows lanes); each block reduces a slab of rows; grid.y = independent row segments
+// (per-sample sums).  Partial results are combined with fp32 atomics into a zeroed / accumulated output.
+__global__ void colsum_kernel(const bf16* __restrict__ x, int ld, long long rows_per_seg, int C8, float* __restrict__ out,
+                              int out_ld) {
+  extern __shared__ float sh[];  // [C8*8]
+  const int seg = blockIdx.y;
+  const bf16* xs = x + static_cast<size_t>(seg) * rows_per_seg * ld;
+  const int cv = threadIdx.x % C8, lane_r = threadIdx.x / C8, nlanes = blockDim.x / C8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (lane_r < nlanes) {
+    for (long long r = static_cast<long long>(blockIdx.x) * nlanes + lane_r; r < rows_per_seg;
+         r += static_cast<long long>(gridDim.x) * nlanes) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(xs + r * ld + cv * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+  }
+  for (int i = threadIdx.x; i < C8 * 8; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  if (lane_r < nlanes) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&sh[cv * 8 + j], acc[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C8 * 8; i += blockDim.x) atomicAdd(&out[static_cast<size_t>(seg) * out_ld + i], sh[i]);
+}
+
+// ---------------------------------------------------------------------------------- weight packing
+__global__ void pack_w_kernel(const float* __restrict__ w, bf16* __restrict__ dst, int Cout, int Cin, int ntaps,
+                              int mode) {
+  const long long n = static_cast<long long>(Cout) * Cin * ntaps;
+  GRID_STRIDE(i, n) {  // i indexes dst
+    int co, ci, tap;
+    if (mode == 0) {  // dst[co][tap][ci]
+      ci = static_cast<int>(i % Cin);
+      tap = static_cast<int>((i / Cin) % ntaps);
+      co = static_cast<int>(i / (static_cast<long long>(Cin) * ntaps));
+    } else {  // dst[ci][ntaps-1-tap][co]
+      co = static_cast<int>(i % Cout);
+      tap = ntaps - 1 - static_cast<int>((i / Cout) % ntaps);
+      ci = static_cast<int>(i / (static_cast<long long>(Cout) * ntaps));
+    }
+    dst[i] = __float2bfloat16(w[(static_cast<long long>(co) * Cin + ci) * ntaps + tap]);
+  }
+}
+
+// ---------------------------------------------------------------------------------- stem conv (Cin <= 4)
+// x: NCHW fp32 (the model input), y: NHWC bf16.  thread = (pixel, 8 output channels); weights in smem.
+__global__ void stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                bf16* __restrict__ y, int B, int Cin, int H, int W, int Cout) {
+  extern __shared__ float sw[];  // [Cout][Cin*9] + bias[Cout]
+  const int K = Cin * 9;
+  for (int i = threadIdx.x; i < Cout * K; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[Cout * K + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int C8 = Cout / 8;
+  const long long n = static_cast<long long>(B) * H * W * C8;
+  GRID_STRIDE(i, n) {
+    const int cg = static_cast<int>(i % C8);
+    long long r = i / C8;
+    const int xw = static_cast<int>(r % W); r /= W;
+    const int yh = static_cast<int>(r % H);
+    const int b = static_cast<int>(r / H);
+    float patch[36];
+    for (int ci = 0; ci < Cin; ++ci)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int hh = yh + t / 3 - 1, ww = xw + t % 3 - 1;
+        patch[ci * 9 + t] = (hh >= 0 && hh < H && ww >= 0 && ww < W)
+                                ? __ldg(x + ((static_cast<size_t>(b) * Cin + ci) * H + hh) * W + ww)
+                                : 0.f;
+      }
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int co = cg * 8 + j;
+      float acc = sw[Cout * K + co];
+      const float* wr = sw + co * K;
+      for (int k = 0; k < K; ++k) acc += patch[k] * wr[k];
+      o[j] = acc;
+    }
+    reinterpret_cast<uint4*>(y)[i] = pack8(o);
+  }
+}
+// dW[co][ci][tap] = sum_pix dY[pix][co] * X[b,ci,pix+tap] ; dbias[co] = sum dY.  thread = output channel.
+__global__ void stem_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ dw,
+                                  float* __restrict__ dbias, int B, int Cin, int H, int W, int Cout, int pix_per_block) {
+  extern __shared__ float sp[];  // [pix_per_block][Cin*9]
+  const int K = Cin * 9;
+  const long long npix = static_cast<long long>(B) * H * W;
+  const long long p0 = static_cast<long long>(blockIdx.x) * pix_per_block;
+  const int np = static_cast<int>(min(static_cast<long long>(pix_per_block), npix - p0));
+  for (int i = threadIdx.x; i < np * K; i += blockDim.x) {
+    const int pi = i / K, k = i - pi * K;
+    const int ci = k / 9, t = k - ci * 9;
+    const long long p = p0 + pi;
+    const int xw = static_cast<int>(p % W), yh = static_cast<int>((p / W) % H), b = static_cast<int>(p / (static_cast<long long>(W) * H));
+    const int hh = yh + t / 3 - 1, ww = xw + t % 3 - 1;
+    sp[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[((static_cast<size_t>(b) * Cin + ci) * H + hh) * W + ww] : 0.f;
+  }
+  __syncthreads();
+  for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
+    float acc[37];
+    for (int k = 0; k <= K; ++k) acc[k] = 0.f;
+    for (int pi = 0; pi < np; ++pi) {
+      const float g = __bfloat162float(dy[(p0 + pi) * Cout + co]);
+      const float* pr = sp + pi * K;
+      for (int k = 0; k < K; ++k) acc[k] += g * pr[k];
+      acc[K] += g;
+    }
+    for (int k = 0; k < K; ++k) atomicAdd(&dw[co * K + k], acc[k]);
+    if (dbias) atomicAdd(&dbias[co], acc[K]);
+  }
+}
+
+// ---------------------------------------------------------------------------------- head conv (Cout <= 8)
+// x: NHWC bf16, y: NCHW fp32 (the model output).  One warp per pixel; lane = 4-channel slice(s) of Cin.
+template <int COUT>
+__global__ void head_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                float* __restrict__ y, int B, int Cin, int H, int W) {
+  extern __shared__ float sw[];  // [tap][co][Cin]
+  for (int i = threadIdx.x; i < 9 * COUT * Cin; i += blockDim.x) {
+    const int c = i % Cin, co = (i / Cin) % COUT, tap = i / (Cin * COUT);
+    sw[i] = w[(co * Cin + c) * 9 + tap];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp_id = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const long long npix = static_cast<long long>(B) * H * W;
+  for (long long p = warp_id; p < npix; p += nwarps) {
+    const int xw = static_cast<int>(p % W), yh = static_cast<int>((p / W) % H);
+    const int b = static_cast<int>(p / (static_cast<long long>(W) * H));
+    float acc[COUT];
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) acc[j] = 0.f;
+    for (int t = 0; t < 9; ++t) {
+      const int hh = yh + t / 3 - 1, ww = xw + t % 3 - 1;
+      if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;  // warp-uniform
+      const bf16* xp = x + ((static_cast<size_t>(b) * H + hh) * W + ww) * Cin;
+      for (int c = lane * 4; c < Cin; c += 128) {
+        const uint2 v = *reinterpret_cast<const uint2*>(xp + c);
+        const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
+        const __nv_bfloat162 h1 = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
+        const float f0 = __low2float(h0), f1 = __high2float(h0), f2 = __low2float(h1), f3 = __high2float(h1);
+#pragma unroll
+        for (int j = 0; j < COUT; ++j) {
+          const float4 wv = *reinterpret_cast<const float4*>(sw + (t * COUT + j) * Cin + c);
+          acc[j] += f0 * wv.x + f1 * wv.y + f2 * wv.z + f3 * wv.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+    }
+    if (lane < COUT) {
+      float v = 0.f;
+#pragma unroll
+      for (int j = 0; j < COUT; ++j)
+        if (lane == j) v = acc[j];
+      y[((static_cast<size_t>(b) * COUT + lane) * H + yh) * W + xw] = v + (bias ? bias[lane] : 0.f);
+    }
+  }
+}
+// dX[pix][c] = sum_{tap,co} dY[b,co,pix-tap] * W[co][c][tap]
+template <int COUT>
+__global__ void head_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, bf16* __restrict__ dx, int B,
+                                  int Cin, int H, int W) {
+  extern __shared__ float sw[];  // [tap][co][Cin]
+  for (int i = threadIdx.x; i < 9 * COUT * Cin; i += blockDim.x) {
+    const int c = i % Cin, co = (i / Cin) % COUT, tap = i / (Cin * COUT);
+    sw[i] = w[(co * Cin + c) * 9 + tap];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp_id = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const long long npix = static_cast<long long>(B) * H * W;
+  for (long long p = warp_id; p < npix; p += nwarps) {
+    const int xw = static_cast<int>(p % W), yh = static_cast<int>((p / W) % H);
+    const int b = static_cast<int>(p / (static_cast<long long>(W) * H));
+    // lane i (and i + 32) fetches dY for (tap = i / COUT, co = i % COUT) at the source pixel of that tap
+    constexpr int NG = 9 * COUT;
+    float g0 = 0.f, g1 = 0.f;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int i = lane + 32 * half;
+      if (i < NG) {
+        const int t = i / COUT, co = i % COUT;
+        const int hh = yh - (t / 3 - 1), ww = xw - (t % 3 - 1);
+        float g = 0.f;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) g = dy[((static_cast<size_t>(b) * COUT + co) * H + hh) * W + ww];
+        if (half == 0) g0 = g; else g1 = g;
+      }
+    }
+    for (int c0 = 0; c0 < Cin; c0 += 128) {  // uniform trip count: every lane takes part in the shuffles
+      const int c = c0 + lane * 4;
+      const bool active = c < Cin;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NG; ++i) {
+        const float gi = i < 32 ? __shfl_sync(0xffffffffu, g0, i) : __shfl_sync(0xffffffffu, g1, i - 32);
+        if (active) {
+          const float4 wv = *reinterpret_cast<const float4*>(sw + i * Cin + c);  // i = tap*COUT + co
+          a0 += gi * wv.x; a1 += gi * wv.y; a2 += gi * wv.z; a3 += gi * wv.w;
+        }
+      }
+      if (active) {
+        uint2 o;
+        *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(a0, a1);
+        *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(a2, a3);
+        *reinterpret_cast<uint2*>(dx + p * Cin + c) = o;
+      }
+    }
+  }
+}
+// dW[co][c][tap] = sum_pix dY[b,co,pix] * X[pix+tap][c] ; thread = input channel c, block = pixel slab
+template <int COUT>
+__global__ void head_wgrad_kernel(const bf16* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
+                                  float* __restrict__ dbias, int B, int Cin, int H, int W, int pix_per_block) {
+  const long long npix = static_cast<long long>(B) * H * W;
+  const long long p0 = static_cast<long long>(blockIdx.x) * pix_per_block;
+  const long long p1 = min(p0 + pix_per_block, npix);
+  for (int c = threadIdx.x; c < Cin; c += blockDim.x) {
+    float acc[COUT * 9];
+    float bacc[COUT];
+#pragma unroll
+    for (int i = 0; i < COUT * 9; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) bacc[j] = 0.f;
+    for (long long p = p0; p < p1; ++p) {
+      const int xw = static_cast<int>(p % W), yh = static_cast<int>((p / W) % H);
+      const int b = static_cast<int>(p / (static_cast<long long>(W) * H));
+      float g[COUT];
+#pragma unroll
+      for (int j = 0; j < COUT; ++j) {
+        g[j] = __ldg(dy + ((static_cast<size_t>(b) * COUT + j) * H + yh) * W + xw);
+        bacc[j] += g[j];
+      }
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int hh = yh + t / 3 - 1, ww = xw + t % 3 - 1;
+        if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+        const float xv = __bfloat162float(x[((static_cast<size_t>(b) * H + hh) * W + ww) * Cin + c]);
+#pragma unroll
+        for (int j = 0; j < COUT; ++j) acc[j * 9 + t] += g[j] * xv;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < COUT; ++j)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) atomicAdd(&dw[(j * Cin + c) * 9 + t], acc[j * 9 + t]);
+    if (c == 0 && dbias) {
+#pragma unroll
+      for (int j = 0; j < COUT; ++j) atomicAdd(&dbias[j], bacc[j]);
+    }
+  }
+}
+
+}  // namespace pddm
+
+using namespace pddm;
+#define S(s_) static_cast<cudaStream_t>(s_)
+
+extern "C" int pddm_nchw_to_nhwc(const float* src, void* dst, int32_t dst_dtype, int32_t B, int32_t C, int32_t HW,
+                                 pddm_stream_t s) {
+  if (!src || !dst || B <= 0 || C <= 0 || HW <= 0) return PDDM_ERR_BAD_ARG;
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  if (dst_dtype == PDDM_BF16) nchw_to_nhwc_kernel<bf16><<<grid, block, 0, S(s)>>>(src, static_cast<bf16*>(dst), C, HW);
+  else nchw_to_nhwc_kernel<float><<<grid, block, 0, S(s)>>>(src, static_cast<float*>(dst), C, HW);
+  return launch_status();
+}
+extern "C" int pddm_nhwc_to_nchw(const void* src, int32_t src_dtype, float* dst, int32_t B, int32_t C, int32_t HW,
+                                 pddm_stream_t s) {
+  if (!src || !dst || B <= 0 || C <= 0 || HW <= 0) return PDDM_ERR_BAD_ARG;
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  if (src_dtype == PDDM_BF16) nhwc_to_nchw_kernel<bf16><<<grid, block, 0, S(s)>>>(static_cast<const bf16*>(src), dst, C, HW);
+  else nhwc_to_nchw_kernel<float><<<grid, block, 0, S(s)>>>(static_cast<const float*>(src), dst, C, HW);
+  return launch_status();
+}
+extern "C" int pddm_copy_channels(const void* src, int32_t ld_src, int32_t src_off, void* dst, int32_t ld_dst,
+                                  int32_t dst_off, int64_t M, int32_t C, pddm_stream_t s) {
+  if (!src || !dst || M <= 0 || C <= 0) return PDDM_ERR_BAD_ARG;
+  if (C % 8 || ld_src % 8 || ld_dst % 8 || src_off % 8 || dst_off % 8 || !aligned16(src) || !aligned16(dst))
+    return PDDM_ERR_UNSUPPORTED;
+  copy_channels_kernel<<<grid_for(M * (C / 8), 256), 256, 0, S(s)>>>(static_cast<const bf16*>(src) + src_off, ld_src,
+                                                                      static_cast<bf16*>(dst) + dst_off, ld_dst, M, C / 8);
+  return launch_status();
+}
+extern "C" int pddm_add_bf16(const void* a, const void* b, void* y, int64_t n, pddm_stream_t s) {
+  if (!a || !b || !y || n <= 0) return PDDM_ERR_BAD_ARG;
+  if (n % 8 || !aligned16(a) || !aligned16(b) || !aligned16(y)) return PDDM_ERR_UNSUPPORTED;
+  add_bf16_kernel<<<grid_for(n / 8, 256), 256, 0, S(s)>>>(static_cast<const uint4*>(a), static_cast<const uint4*>(b),
+                                                          static_cast<uint4*>(y), n / 8);
+  return launch_status();
+}
+extern "C" int pddm_upsample2x(const void* src, void* dst, int32_t B, int32_t H, int32_t W, int32_t C, pddm_stream_t s) {
+  if (!src || !dst || B <= 0 || H <= 0 || W <= 0 || C <= 0) return PDDM_ERR_BAD_ARG;
+  if (C % 8) return PDDM_ERR_UNSUPPORTED;
+  upsample2x_kernel<<<grid_for(static_cast<long long>(B) * 4 * H * W * (C / 8), 256), 256, 0, S(s)>>>(
+      static_cast<const bf16*>(src), static_cast<bf16*>(dst), B, H, W, C / 8);
+  return launch_status();
+}
+extern "C" int pddm_upsample2x_bwd(const void* gd, void* gs, int32_t B, int32_t H, int32_t W, int32_t C,
+                                   pddm_stream_t s) {
+  if (!gd || !gs || B <= 0 || H <= 0 || W <= 0 || C <= 0) return PDDM_ERR_BAD_ARG;
+  if (C % 8) return PDDM_ERR_UNSUPPORTED;
+  upsample2x_bwd_kernel<<<grid_for(static_cast<long long>(B) * H * W * (C / 8), 256), 256, 0, S(s)>>>(
+      static_cast<const bf16*>(gd), static_cast<bf16*>(gs), B, H, W, C / 8);
+  return launch_status();
+}
+extern "C" int pddm_phase_split(const void* src, void* dst, int32_t B, int32_t H, int32_t W, int32_t C, pddm_stream_t s) {
+  if (!src || !dst || B <= 0 || H <= 0 || W <= 0 || C <= 0) return PDDM_ERR_BAD_ARG;
+  if (C % 8 || H % 2 || W % 2) return PDDM_ERR_UNSUPPORTED;
+  phase_kernel<true><<<grid_for(static_cast<long long>(B) * H * W * (C / 8), 256), 256, 0, S(s)>>>(
+      static_cast<const bf16*>(src), static_cast<bf16*>(dst), B, H, W, C / 8);
+  return launch_status();
+}
+extern "C" int pddm_phase_merge(const void* src, void* dst, int32_t B, int32_t H, int32_t W, int32_t C, pddm_stream_t s) {
+  if (!src || !dst || B <= 0 || H <= 0 || W <= 0 || C <= 0) return PDDM_ERR_BAD_ARG;
+  if (C % 8 || H % 2 || W % 2) return PDDM_ERR_UNSUPPORTED;
+  phase_kernel<false><<<grid_for(static_cast<long long>(B) * H * W * (C / 8), 256), 256, 0, S(s)>>>(
+      static_cast<const bf16*>(src), static_cast<bf16*>(dst), B, H, W, C / 8);
+  return launch_status();
+}
+extern "C" int pddm_convert(const void* x, int32_t x_dtype, void* y, int32_t y_dtype, int64_t n, pddm_stream_t s) {
+  if (!x || !y || n <= 0) return PDDM_ERR_BAD_ARG;
+  const int g = grid_for(n, 256);
+  if (x_dtype == PDDM_F32 && y_dtype == PDDM_BF16)
+    convert_kernel<float, bf16><<<g, 256, 0, S(s)>>>(static_cast<const float*>(x), static_cast<bf16*>(y), n);
+  else if (x_dtype == PDDM_BF16 && y_dtype == PDDM_F32)
+    convert_kernel<bf16, float><<<g, 256, 0, S(s)>>>(static_cast<const bf16*>(x), static_cast<float*>(y), n);
+  else
+    return PDDM_ERR_UNSUPPORTED;
+  return launch_status();
+}
+extern "C" int pddm_silu(const float* x, void* y, int32_t y_dtype, int64_t n, pddm_stream_t s) {
+  if (!x || !y || n <= 0) return PDDM_ERR_BAD_ARG;
+  silu_kernel<<<grid_for(n, 256), 256, 0, S(s)>>>(x, y, y_dtype, n);
+  return launch_status();
+}
+extern "C" int pddm_silu_bwd(const float* x, const float* dy, float* dx, int64_t n, pddm_stream_t s) {
+  if (!x || !dy || !dx || n <= 0) return PDDM_ERR_BAD_ARG;
+  silu_bwd_kernel<<<grid_for(n, 256), 256, 0, S(s)>>>(x, dy, dx, n);
+  return launch_status();
+}
+
+static int colsum_launch(const void* x, int ld, long long rows_per_seg, int segs, int C, float* out, int out_ld,
+                         int accumulate, cudaStream_t s) {
+  if (C % 8 || ld % 8 || !aligned16(x) || C > 8192) return PDDM_ERR_UNSUPPORTED;
+  const int C8 = C / 8;
+  int threads = C8 * (256 / C8 > 0 ? 256 / C8 : 1);
+  if (threads > 1024) return PDDM_ERR_UNSUPPORTED;
+  const int nlanes = threads / C8;
+  long long gx = (rows_per_seg + static_cast<long long>(nlanes) * 16 - 1) / (static_cast<long long>(nlanes) * 16);
+  const long long cap = 2LL * 148 / (segs < 296 ? segs : 296) + 1;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  if (!accumulate) {
+    if (out_ld == C) {
+      if (cudaMemsetAsync(out, 0, static_cast<size_t>(segs) * C * sizeof(float), s) != cudaSuccess) return PDDM_ERR_CUDA;
+    } else {
+      for (int i = 0; i < segs; ++i)
+        if (cudaMemsetAsync(out + static_cast<size_t>(i) * out_ld, 0, C * sizeof(float), s) != cudaSuccess)
+          return PDDM_ERR_CUDA;
+    }
+  }
+  dim3 grid(static_cast<unsigned>(gx), segs);
+  colsum_kernel<<<grid, threads, C * sizeof(float), s>>>(static_cast<const bf16*>(x), ld, rows_per_seg, C8, out, out_ld);
+  return launch_status();
+}
+extern "C" int pddm_colsum(const void* x, int32_t ld, int64_t M, int32_t C, float* out, int32_t accumulate,
+                           pddm_stream_t s) {
+  if (!x || !out || M <= 0 || C <= 0) return PDDM_ERR_BAD_ARG;
+  return colsum_launch(x, ld, M, 1, C, out, C, accumulate, S(s));
+}
+extern "C" int pddm_colsum_per_sample(const void* x, int32_t B, int32_t HW, int32_t C, float* out, pddm_stream_t s) {
+  if (!x || !out || B <= 0 || HW <= 0 || C <= 0) return PDDM_ERR_BAD_ARG;
+  return colsum_launch(x, C, HW, B, C, out, C, 0, S(s));
+}
+extern "C" int pddm_pack_conv_weight(const float* w, void* dst, int32_t Cout, int32_t Cin, int32_t ntaps, int32_t mode,
+                                     pddm_stream_t s) {
+  if (!w || !dst || Cout <= 0 || Cin <= 0 || ntaps <= 0 || mode < 0 || mode > 1) return PDDM_ERR_BAD_ARG;
+  pack_w_kernel<<<grid_for(static_cast<long long>(Cout) * Cin * ntaps, 256), 256, 0, S(s)>>>(
+      w, static_cast<bf16*>(dst), Cout, Cin, ntaps, mode);
+  return launch_status();
+}
+
+extern "C" int pddm_stem_conv_fwd(const float* x, const float* w, const float* bias, void* y, int32_t B, int32_t Cin,
+                                  int32_t H, int32_t W, int32_t Cout, pddm_stream_t s) {
+  if (!x || !w || !y || B <= 0 || H <= 0 || W <= 0) return PDDM_ERR_BAD_ARG;
+  if (Cin < 1 || Cin > 4 || Cout % 8 || Cout > 1024) return PDDM_ERR_UNSUPPORTED;
+  const size_t smem = (static_cast<size_t>(Cout) * Cin * 9 + Cout) * sizeof(float);
+  stem_fwd_kernel<<<grid_for(static_cast<long long>(B) * H * W * (Cout / 8), 256), 256, smem, S(s)>>>(
+      x, w, bias, static_cast<bf16*>(y), B, Cin, H, W, Cout);
+  return launch_status();
+}
+extern "C" int pddm_stem_conv_wgrad(const float* x, const void* dy, float* dw, float* dbias, int32_t B, int32_t Cin,
+                                    int32_t H, int32_t W, int32_t Cout, pddm_stream_t s) {
+  if (!x || !dy || !dw || B <= 0 || H <= 0 || W <= 0) return PDDM_ERR_BAD_ARG;
+  if (Cin < 1 || Cin > 4 || Cout > 1024) return PDDM_ERR_UNSUPPORTED;
+  if (cudaMemsetAsync(dw, 0, static_cast<size_t>(Cout) * Cin * 9 * sizeof(float), S(s)) != cudaSuccess) return PDDM_ERR_CUDA;
+  if (dbias && cudaMemsetAsync(dbias, 0, Cout * sizeof(float), S(s)) != cudaSuccess) return PDDM_ERR_CUDA;
+  const int ppb = 256;
+  const long long npix = static_cast<long long>(B) * H * W;
+  const int blocks = static_cast<int>((npix + ppb - 1) / ppb);
+  const int threads = Cout < 128 ? ((Cout + 31) / 32 * 32) : 128;
+  stem_wgrad_kernel<<<blocks, threads, static_cast<size_t>(ppb) * Cin * 9 * sizeof(float), S(s)>>>(
+      x, static_cast<const bf16*>(dy), dw, dbias, B, Cin, H, W, Cout, ppb);
+  return launch_status();
+}
+
+template <int COUT>
+static int head_fwd_t(const void* x, const float* w, const float* bias, float* y, int B, int Cin, int H, int W,
+                      cudaStream_t s) {
+  const size_t smem = static_cast<size_t>(9) * COUT * Cin * sizeof(float);
+  if (smem > 48 * 1024) {
+    if (cudaFuncSetAttribute(head_fwd_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) !=
+        cudaSuccess)
+      return PDDM_ERR_UNSUPPORTED;
+  }
+  head_fwd_kernel<COUT><<<grid_for(static_cast<long long>(B) * H * W * 4, 256), 256, smem, s>>>(
+      static_cast<const bf16*>(x), w, bias, y, B, Cin, H, W);
+  return launch_status();
+}
+extern "C" int pddm_head_conv_fwd(const void* x, const float* w, const float* bias, float* y, int32_t B, int32_t Cin,
+                                  int32_t H, int32_t W, int32_t Cout, pddm_stream_t s) {
+  if (!x || !w || !y || B <= 0 || H <= 0 || W <= 0) return PDDM_ERR_BAD_ARG;
+  if (Cin % 4 || Cin > 1024) return PDDM_ERR_UNSUPPORTED;
+  switch (Cout) {
+    case 1: return head_fwd_t<1>(x, w, bias, y, B, Cin, H, W, S(s));
+    case 2: return head_fwd_t<2>(x, w, bias, y, B, Cin, H, W, S(s));
+    case 3: return head_fwd_t<3>(x, w, bias, y, B, Cin, H, W, S(s));
+    case 6: return head_fwd_t<6>(x, w, bias, y, B, Cin, H, W, S(s));
+    default: return PDDM_ERR_UNSUPPORTED;
+  }
+}
+template <int COUT>
+static int head_bwd_t(const void* x, const float* w, const float* dy, void* dx, float* dw, float* dbias, int B, int Cin,
+                      int H, int W, cudaStream_t s) {
+  const size_t smem = static_cast<size_t>(9) * COUT * Cin * sizeof(float);
+  if (dx) {
+    if (smem > 48 * 1024) {
+      if (cudaFuncSetAttribute(head_dgrad_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(smem)) != cudaSuccess)
+        return PDDM_ERR_UNSUPPORTED;
+    }
+    head_dgrad_kernel<COUT><<<grid_for(static_cast<long long>(B) * H * W * 4, 256), 256, smem, s>>>(
+        dy, w, static_cast<bf16*>(dx), B, Cin, H, W);
+    if (cudaPeekAtLastError() != cudaSuccess) return PDDM_ERR_CUDA;
+  }
+  if (dw) {
+    if (cudaMemsetAsync(dw, 0, static_cast<size_t>(COUT) * Cin * 9 * sizeof(float), s) != cudaSuccess) return PDDM_ERR_CUDA;
+    if (dbias && cudaMemsetAsync(dbias, 0, COUT * sizeof(float), s) != cudaSuccess) return PDDM_ERR_CUDA;
+    const long long npix = static_cast<long long>(B) * H * W;
+    int blocks = 4 * (device_info().sm_count > 0 ? device_info().sm_count : 148);
+    int ppb = static_cast<int>((npix + blocks - 1) / blocks);
+    if (ppb < 16) ppb = 16;
+    blocks = static_cast<int>((npix + ppb - 1) / ppb);
+    const int threads = Cin < 128 ? ((Cin + 31) / 32 * 32) : 128;
+    head_wgrad_kernel<COUT><<<blocks, threads, 0, s>>>(static_cast<const bf16*>(x), dy, dw, dbias, B, Cin, H, W, ppb);
+  }
+  return launch_status();
+}
+extern "C" int pddm_head_conv_bwd(const void* x, const float* w, const float* dy, void* dx, float* dw, float* dbias,
+                                  int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t Cout, pddm_stream_t s) {
+  if (!x || !w || !dy || B <= 0 || H <= 0 || W <= 0) return PDDM_ERR_BAD_ARG;
+  if (Cin % 4 || Cin > 1024) return PDDM_ERR_UNSUPPORTED;
+  switch (Cout) {
+    case 1: return head_bwd_t<1>(x, w, dy, dx, dw, dbias, B, Cin, H, W, S(s));
+    case 2: return head_bwd_t<2>(x, w, dy, dx, dw, dbias, B, Cin, H, W, S(s));
+    case 3: return head_bwd_t<3>(x, w, dy, dx, dw, dbias, B, Cin, H, W, S(s));
+    case 6: return head_bwd_t<6>(x, w, dy, dx, dw, dbias, B, Cin, H, W, S(s));
+    default: return PDDM_ERR_UNSUPPORTED;
+  }
+}

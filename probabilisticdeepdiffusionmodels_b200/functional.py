@@ -1,0 +1,488 @@
+"""Host-side launch helpers: torch tensors in, C-ABI kernel calls out (no autograd here; see ops.py).
+
+Activation convention inside the network: contiguous ``[B, H, W, C]`` (NHWC) tensors, bf16 unless noted.
+Every function only enqueues work on the current CUDA stream (capturable in a CUDA graph).
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib as L
+
+bf16 = torch.bfloat16
+f32 = torch.float32
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _chk(t, dtype=None):
+    if not t.is_cuda:
+        raise RuntimeError("pddm_b200 ops need CUDA tensors (sm_100a); there is no CPU fallback")
+    if not t.is_contiguous():
+        raise RuntimeError("pddm_b200 ops need contiguous tensors")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"expected {dtype}, got {t.dtype}")
+    return t
+
+
+# ------------------------------------------------------------------------------------------ tap tables
+def taps_3x3():
+    return [(0, r - 1, s - 1, r * 3 + s) for r in range(3) for s in range(3)]
+
+
+def taps_1x1():
+    return [(0, 0, 0, 0)]
+
+
+def taps_stride2(B):
+    """3x3 / stride 2 / pad 1 over the phase-split input [4B, H/2, W/2, C] (phase p = 2*(row parity)+(col parity))."""
+    out = []
+    for r in range(3):
+        for s in range(3):
+            a, dh = (0, 0) if r == 1 else (1, -1 if r == 0 else 0)
+            b, dw = (0, 0) if s == 1 else (1, -1 if s == 0 else 0)
+            out.append(((a * 2 + b) * B, dh, dw, r * 3 + s))
+    return out
+
+
+def taps_stride2_dgrad(a, b):
+    """Taps of the stride-2 data gradient for output phase (a, b): dX[2i+a, 2j+b] = sum dY[i+di, j+dj] W[r, s];
+    weight slots refer to the mode-1 (flipped) pack, where tap (r, s) lives in slot 8 - (3r + s)."""
+    rows = [(1, 0)] if a == 0 else [(0, 1), (2, 0)]
+    cols = [(1, 0)] if b == 0 else [(0, 1), (2, 0)]
+    return [(0, di, dj, 8 - (r * 3 + s)) for r, di in rows for s, dj in cols]
+
+
+def _fill_taps(p, taps):
+    p.ntaps = len(taps)
+    for i, (db, dh, dw, slot) in enumerate(taps):
+        p.tap_db[i], p.tap_dh[i], p.tap_dw[i] = db, dh, dw
+        if hasattr(p, "tap_w"):
+            p.tap_w[i] = slot
+
+
+# ------------------------------------------------------------------------------------------ conv / linear
+def pack_weight(w, mode):
+    """fp32 [Cout, Cin, *k] -> bf16 GEMM operand.  mode 0: [Cout, taps, Cin]; mode 1 (dgrad): [Cin, taps(flipped), Cout]."""
+    L.require_device(w)
+    _chk(w, f32)
+    cout, cin = w.shape[0], w.shape[1]
+    ntaps = w.numel() // (cout * cin)
+    dst = torch.empty((cout, ntaps, cin) if mode == 0 else (cin, ntaps, cout), dtype=bf16, device=w.device)
+    L.call("pddm_pack_conv_weight", L.ptr(w), L.ptr(dst), cout, cin, ntaps, mode, L.stream())
+    return dst
+
+
+def tap_gemm(x, wp, taps, B, H, W, *, bias=None, bcast=None, residual=None, out=None, out_dtype=bf16,
+             out_hw=None, out_map=(1, 1, 0, 0), cin=None):
+    """y[b, oh, ow, :] = sum_taps x[b+db, h+dh, w+dw, :] @ wp[:, slot, :]^T (+bias +bcast[b] +residual).
+
+    x: bf16 [NB, H, W, ldx] (cin <= ldx leading channels used); wp: bf16 [Cout, slots, cin]."""
+    L.require_device(x)
+    _chk(x, bf16)
+    _chk(wp, bf16)
+    NB, ldx = x.shape[0], x.shape[-1]
+    cout, slots, wcin = wp.shape
+    cin = wcin if cin is None else cin
+    assert wcin == cin and x.shape[1] == H and x.shape[2] == W
+    oH, oW = out_hw if out_hw is not None else (H, W)
+    if out is None:
+        out = torch.empty((B, oH, oW, cout), dtype=out_dtype, device=x.device)
+    p = L.ConvParams()
+    p.x, p.w, p.y = L.ptr(x), L.ptr(wp), L.ptr(out)
+    p.bias = L.ptr(_chk(bias, f32)) if bias is not None else None
+    if bcast is not None:
+        _chk(bcast, f32)
+        p.bcast, p.ld_bcast = L.ptr(bcast), bcast.shape[-1]
+    if residual is not None:
+        _chk(residual)
+        assert residual.shape == out.shape
+        p.residual, p.res_dtype = L.ptr(residual), L.dt(residual)
+    p.y_dtype = L.dt(out)
+    p.x_NB, p.B, p.H, p.W, p.Cin, p.ldx, p.Cout = NB, B, H, W, cin, ldx, cout
+    _fill_taps(p, taps)
+    p.w_ntaps = slots
+    p.out_H, p.out_W = oH, oW
+    p.out_sh, p.out_sw, p.out_oh, p.out_ow = out_map
+    L.call("pddm_conv2d_fwd", C.byref(p), L.stream())
+    return out
+
+
+def tap_wgrad(x, dy, taps, B, H, W, cin, cout, w_shape, accumulate_into=None):
+    """dw[n, c, tap] = sum_pixels dy[b,h,w,n] * x[b+db, h+dh, w+dw, c]  -> fp32 tensor of shape w_shape."""
+    L.require_device(x)
+    _chk(x, bf16)
+    _chk(dy, bf16)
+    dw = accumulate_into if accumulate_into is not None else torch.empty(w_shape, dtype=f32, device=x.device)
+    p = L.WgradParams()
+    p.x, p.dy, p.dw = L.ptr(x), L.ptr(dy), L.ptr(dw)
+    p.x_NB, p.B, p.H, p.W, p.Cin, p.ldx, p.Cout, p.lddy = x.shape[0], B, H, W, cin, x.shape[-1], cout, dy.shape[-1]
+    _fill_taps(p, taps)
+    p.dw_layout = 1
+    p.accumulate = 1 if accumulate_into is not None else 0
+    nbytes = L.load().pddm_conv2d_wgrad_workspace(C.byref(p))
+    ws = _ws(nbytes, x.device)
+    L.call("pddm_conv2d_wgrad", C.byref(p), L.ptr(ws), C.c_size_t(ws.numel()), L.stream())
+    return dw
+
+
+def colsum(x2d_bf16, C_):
+    """sum over all leading dims of a bf16 [..., C] tensor -> fp32 [C]."""
+    _chk(x2d_bf16, bf16)
+    out = torch.empty(C_, dtype=f32, device=x2d_bf16.device)
+    M = x2d_bf16.numel() // x2d_bf16.shape[-1]
+    L.call("pddm_colsum", L.ptr(x2d_bf16), x2d_bf16.shape[-1], C.c_int64(M), C_, L.ptr(out), 0, L.stream())
+    return out
+
+
+def colsum_per_sample(x):
+    """bf16 [B, ..., C] -> fp32 [B, C]."""
+    _chk(x, bf16)
+    B, C_ = x.shape[0], x.shape[-1]
+    out = torch.empty((B, C_), dtype=f32, device=x.device)
+    L.call("pddm_colsum_per_sample", L.ptr(x), B, x.numel() // (B * C_), C_, L.ptr(out), L.stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------ layout helpers
+def nchw_to_nhwc(x, dtype=bf16):
+    L.require_device(x)
+    _chk(x, f32)
+    B, C_, H, W = x.shape
+    y = torch.empty((B, H, W, C_), dtype=dtype, device=x.device)
+    L.call("pddm_nchw_to_nhwc", L.ptr(x), L.ptr(y), L.dt(y), B, C_, H * W, L.stream())
+    return y
+
+
+def nhwc_to_nchw(x):
+    L.require_device(x)
+    _chk(x)
+    B, H, W, C_ = x.shape
+    y = torch.empty((B, C_, H, W), dtype=f32, device=x.device)
+    L.call("pddm_nhwc_to_nchw", L.ptr(x), L.dt(x), L.ptr(y), B, C_, H * W, L.stream())
+    return y
+
+
+def copy_channels(src, src_off, dst, dst_off, nch):
+    M = src.numel() // src.shape[-1]
+    L.call("pddm_copy_channels", L.ptr(src), src.shape[-1], src_off, L.ptr(dst), dst.shape[-1], dst_off,
+           C.c_int64(M), nch, L.stream())
+
+
+def concat_channels(a, b):
+    """th.cat([a, b], dim=channels) for NHWC bf16 (src/modules/unet.py:492)."""
+    _chk(a, bf16)
+    _chk(b, bf16)
+    out = torch.empty(a.shape[:-1] + (a.shape[-1] + b.shape[-1],), dtype=bf16, device=a.device)
+    copy_channels(a, 0, out, 0, a.shape[-1])
+    copy_channels(b, 0, out, a.shape[-1], b.shape[-1])
+    return out
+
+
+def split_channels(x, c1):
+    a = torch.empty(x.shape[:-1] + (c1,), dtype=bf16, device=x.device)
+    b = torch.empty(x.shape[:-1] + (x.shape[-1] - c1,), dtype=bf16, device=x.device)
+    copy_channels(x, 0, a, 0, c1)
+    copy_channels(x, c1, b, 0, x.shape[-1] - c1)
+    return a, b
+
+
+def upsample2x(x):
+    B, H, W, C_ = x.shape
+    y = torch.empty((B, 2 * H, 2 * W, C_), dtype=bf16, device=x.device)
+    L.call("pddm_upsample2x", L.ptr(_chk(x, bf16)), L.ptr(y), B, H, W, C_, L.stream())
+    return y
+
+
+def upsample2x_bwd(g):
+    B, H2, W2, C_ = g.shape
+    y = torch.empty((B, H2 // 2, W2 // 2, C_), dtype=bf16, device=g.device)
+    L.call("pddm_upsample2x_bwd", L.ptr(_chk(g, bf16)), L.ptr(y), B, H2 // 2, W2 // 2, C_, L.stream())
+    return y
+
+
+def phase_split(x):
+    B, H, W, C_ = x.shape
+    y = torch.empty((4 * B, H // 2, W // 2, C_), dtype=bf16, device=x.device)
+    L.call("pddm_phase_split", L.ptr(_chk(x, bf16)), L.ptr(y), B, H, W, C_, L.stream())
+    return y
+
+
+def add_bf16(a, b):
+    y = torch.empty_like(a)
+    L.call("pddm_add_bf16", L.ptr(_chk(a, bf16)), L.ptr(_chk(b, bf16)), L.ptr(y), C.c_int64(a.numel()), L.stream())
+    return y
+
+
+def convert(x, dtype):
+    """fp32 <-> bf16 elementwise conversion (our own kernel: no torch math on the hot path)."""
+    if x.dtype == dtype:
+        return x
+    _chk(x)
+    y = torch.empty(x.shape, dtype=dtype, device=x.device)
+    L.call("pddm_convert", L.ptr(x), L.dt(x), L.ptr(y), L.dt(y), C.c_int64(x.numel()), L.stream())
+    return y
+
+
+def silu_vec(x, dtype=bf16):
+    y = torch.empty(x.shape, dtype=dtype, device=x.device)
+    L.call("pddm_silu", L.ptr(_chk(x, f32)), L.ptr(y), L.dt(y), C.c_int64(x.numel()), L.stream())
+    return y
+
+
+def silu_vec_bwd(x, dy):
+    dx = torch.empty_like(x)
+    L.call("pddm_silu_bwd", L.ptr(_chk(x, f32)), L.ptr(_chk(dy, f32)), L.ptr(dx), C.c_int64(x.numel()), L.stream())
+    return dx
+
+
+def timestep_embedding(t, dim, max_period=10000, dtype=bf16):
+    """src/modules/nn.py:104-122; t int64 or float32 [B]."""
+    L.require_device(t)
+    if t.dtype not in (torch.int64, torch.float32):
+        t = t.float() if t.is_floating_point() else t.long()
+    t = t.contiguous()
+    out = torch.empty((t.shape[0], dim), dtype=dtype, device=t.device)
+    L.call("pddm_timestep_embedding", L.ptr(t), 1 if t.dtype == torch.float32 else 0, L.ptr(out), L.dt(out),
+           t.shape[0], dim, C.c_float(float(max_period)), L.stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------ group norm
+def gn_silu_fwd(x, gamma, beta, groups=32, eps=1e-5, silu=True, scale=None, shift=None):
+    """x: [B, ..., C] bf16/fp32 -> (y bf16, mean [B,G], rstd [B,G])."""
+    L.require_device(x)
+    _chk(x)
+    B, C_ = x.shape[0], x.shape[-1]
+    HW = x.numel() // (B * C_)
+    y = torch.empty(x.shape, dtype=bf16, device=x.device)
+    mean = torch.empty((B, groups), dtype=f32, device=x.device)
+    rstd = torch.empty((B, groups), dtype=f32, device=x.device)
+    p = L.GnFwdParams()
+    p.x, p.x_dtype, p.gamma, p.beta, p.y, p.mean, p.rstd = L.ptr(x), L.dt(x), L.ptr(gamma), L.ptr(beta), L.ptr(y), \
+        L.ptr(mean), L.ptr(rstd)
+    if scale is not None:
+        p.scale, p.shift, p.ld_ss = L.ptr(scale), L.ptr(shift), scale.stride(0)
+    p.B, p.HW, p.C, p.G, p.eps, p.silu = B, HW, C_, groups, eps, 1 if silu else 0
+    ws = _ws(L.load().pddm_gn_silu_fwd_workspace(B, groups), x.device)
+    L.call("pddm_gn_silu_fwd", C.byref(p), L.ptr(ws), C.c_size_t(ws.numel()), L.stream())
+    return y, mean, rstd
+
+
+def gn_silu_bwd(x, dy, gamma, beta, mean, rstd, groups=32, silu=True, scale=None, shift=None, dx_dtype=bf16,
+                want_colsum=False):
+    """-> dx, dgamma, dbeta, dx_colsum [B,C] | None, dscale, dshift"""
+    _chk(x)
+    _chk(dy, bf16)
+    B, C_ = x.shape[0], x.shape[-1]
+    HW = x.numel() // (B * C_)
+    dev = x.device
+    dx = torch.empty(x.shape, dtype=dx_dtype, device=dev)
+    dgamma = torch.empty(C_, dtype=f32, device=dev)
+    dbeta = torch.empty(C_, dtype=f32, device=dev)
+    colsum_ = torch.empty((B, C_), dtype=f32, device=dev) if want_colsum else None
+    dscale = dshift = None
+    p = L.GnBwdParams()
+    p.x, p.x_dtype, p.dy, p.gamma, p.beta, p.mean, p.rstd = L.ptr(x), L.dt(x), L.ptr(dy), L.ptr(gamma), L.ptr(beta), \
+        L.ptr(mean), L.ptr(rstd)
+    if scale is not None:
+        dscale = torch.empty((B, C_), dtype=f32, device=dev)
+        dshift = torch.empty((B, C_), dtype=f32, device=dev)
+        p.scale, p.shift, p.ld_ss = L.ptr(scale), L.ptr(shift), scale.stride(0)
+        assert scale.stride(0) == C_ or True
+        # dscale/dshift are written with the same leading dimension as scale/shift
+        if scale.stride(0) != C_:
+            dscale = torch.empty((B, scale.stride(0)), dtype=f32, device=dev)
+            dshift = torch.empty((B, scale.stride(0)), dtype=f32, device=dev)
+        p.dscale, p.dshift = L.ptr(dscale), L.ptr(dshift)
+    p.dx, p.dx_dtype, p.dgamma, p.dbeta = L.ptr(dx), L.dt(dx), L.ptr(dgamma), L.ptr(dbeta)
+    p.dx_colsum = L.ptr(colsum_)
+    p.B, p.HW, p.C, p.G, p.silu = B, HW, C_, groups, 1 if silu else 0
+    ws = _ws(L.load().pddm_gn_silu_bwd_workspace(B, C_), dev)
+    L.call("pddm_gn_silu_bwd", C.byref(p), L.ptr(ws), C.c_size_t(ws.numel()), L.stream())
+    return dx, dgamma, dbeta, colsum_, dscale, dshift
+
+
+# ------------------------------------------------------------------------------------------ attention
+def attn_fwd(qkv, heads):
+    """qkv: bf16 [B, T, 3C] head-major [q|k|v] packing (src/modules/unet.py:230) -> (out [B,T,C], lse [B,heads,T])."""
+    L.require_device(qkv)
+    _chk(qkv, bf16)
+    B, T, C3 = qkv.shape
+    Cc = C3 // 3
+    out = torch.empty((B, T, Cc), dtype=bf16, device=qkv.device)
+    lse = torch.empty((B, heads, T), dtype=f32, device=qkv.device)
+    p = L.AttnFwdParams()
+    p.qkv, p.out, p.lse, p.B, p.T, p.heads, p.d = L.ptr(qkv), L.ptr(out), L.ptr(lse), B, T, heads, Cc // heads
+    L.call("pddm_attn_fwd", C.byref(p), L.stream())
+    return out, lse
+
+
+def attn_bwd(qkv, out, dout, lse, heads):
+    _chk(dout, bf16)
+    B, T, C3 = qkv.shape
+    dqkv = torch.empty_like(qkv)
+    p = L.AttnBwdParams()
+    p.qkv, p.out, p.dout, p.lse, p.dqkv = L.ptr(qkv), L.ptr(out), L.ptr(dout), L.ptr(lse), L.ptr(dqkv)
+    p.B, p.T, p.heads, p.d = B, T, heads, C3 // 3 // heads
+    L.call("pddm_attn_bwd", C.byref(p), L.stream())
+    return dqkv
+
+
+# ------------------------------------------------------------------------------------------ thin convs
+def stem_conv_fwd(x_nchw, w, bias):
+    L.require_device(x_nchw)
+    _chk(x_nchw, f32)
+    B, Cin, H, W = x_nchw.shape
+    y = torch.empty((B, H, W, w.shape[0]), dtype=bf16, device=x_nchw.device)
+    L.call("pddm_stem_conv_fwd", L.ptr(x_nchw), L.ptr(_chk(w, f32)), L.ptr(bias), L.ptr(y), B, Cin, H, W, w.shape[0],
+           L.stream())
+    return y
+
+
+def stem_conv_wgrad(x_nchw, dy, w_shape):
+    B, Cin, H, W = x_nchw.shape
+    dw = torch.empty(w_shape, dtype=f32, device=dy.device)
+    db = torch.empty(w_shape[0], dtype=f32, device=dy.device)
+    L.call("pddm_stem_conv_wgrad", L.ptr(x_nchw), L.ptr(_chk(dy, bf16)), L.ptr(dw), L.ptr(db), B, Cin, H, W,
+           w_shape[0], L.stream())
+    return dw, db
+
+
+def head_conv_fwd(x, w, bias):
+    L.require_device(x)
+    _chk(x, bf16)
+    B, H, W, Cin = x.shape
+    y = torch.empty((B, w.shape[0], H, W), dtype=f32, device=x.device)
+    L.call("pddm_head_conv_fwd", L.ptr(x), L.ptr(_chk(w, f32)), L.ptr(bias), L.ptr(y), B, Cin, H, W, w.shape[0],
+           L.stream())
+    return y
+
+
+def head_conv_bwd(x, w, dy_nchw):
+    B, H, W, Cin = x.shape
+    dx = torch.empty_like(x)
+    dw = torch.empty(w.shape, dtype=f32, device=x.device)
+    db = torch.empty(w.shape[0], dtype=f32, device=x.device)
+    L.call("pddm_head_conv_bwd", L.ptr(x), L.ptr(w), L.ptr(_chk(dy_nchw, f32)), L.ptr(dx), L.ptr(dw), L.ptr(db), B, Cin,
+           H, W, w.shape[0], L.stream())
+    return dx, dw, db
+
+
+# ------------------------------------------------------------------------------------------ diffusion math
+class DeviceTables:
+    """The Engine's fp32 coefficient tables resident on one device (built once; src/engine.py:121-150)."""
+
+    def __init__(self, tables_cpu, device):
+        self.T = int(tables_cpu["betas"].shape[0])
+        pv = tables_cpu["posterior_variance"]
+        extra = {
+            "posterior_log_variance_clipped": torch.log(torch.cat([pv[1:2], pv[1:]])) if self.T > 1 else torch.log(pv),
+            "log_betas": torch.log(tables_cpu["betas"]),
+        }
+        self.t = {k: v.to(device=device, dtype=f32).contiguous() for k, v in {**tables_cpu, **extra}.items()}
+        self.device = torch.device(device)
+
+    def struct(self):
+        s = L.Tables()
+        for name, _ in L.Tables._fields_:
+            if name != "T":
+                setattr(s, name, L.ptr(self.t[name]))
+        s.T = self.T
+        return s
+
+
+def q_sample(x0, noise, t, tabs: DeviceTables):
+    L.require_device(x0)
+    _chk(x0, f32)
+    _chk(noise, f32)
+    out = torch.empty_like(x0)
+    p = L.QSampleParams()
+    p.x0, p.noise, p.x_t = L.ptr(x0), L.ptr(noise), L.ptr(out)
+    if isinstance(t, int):
+        p.t, p.t_const = None, t
+    else:
+        t = t.to(device=x0.device, dtype=torch.int64).contiguous()
+        if t.numel() == 1 and x0.shape[0] != 1:
+            t = t.expand(x0.shape[0]).contiguous()
+        p.t = L.ptr(t)
+    p.alphas_hat_sqrt, p.one_min_alphas_hat_sqrt = L.ptr(tabs.t["alphas_hat_sqrt"]), L.ptr(tabs.t["one_min_alphas_hat_sqrt"])
+    p.B, p.chw = x0.shape[0], x0.numel() // x0.shape[0]
+    L.call("pddm_q_sample", C.byref(p), L.stream())
+    return out
+
+
+def sq_err(pred, noise, gscale=None, want_grad=False):
+    """per-sample mean (noise - pred[:, :C])^2 ; optionally d/dpred scaled by gscale[b] (other channels zero)."""
+    L.require_device(pred)
+    _chk(pred, f32)
+    _chk(noise, f32)
+    B, Cc = noise.shape[0], noise.shape[1]
+    hw = noise.numel() // (B * Cc)
+    per = torch.empty(B, dtype=f32, device=pred.device)
+    grad = None
+    p = L.SqErrParams()
+    p.pred, p.noise, p.per_sample = L.ptr(pred), L.ptr(noise), L.ptr(per)
+    if want_grad:
+        grad = torch.zeros_like(pred) if pred.shape[1] != Cc else torch.empty_like(pred)
+        p.grad_pred, p.gscale = L.ptr(grad), L.ptr(_chk(gscale, f32))
+    p.B, p.C, p.c_total, p.hw = B, Cc, pred.shape[1], hw
+    L.call("pddm_sq_err", C.byref(p), L.stream())
+    return per, grad
+
+
+SIGMA_MODES = {"beta": 0, "beta_tilde": 1, "learned": 2}
+
+
+def p_sample_step(x_t, model_out, z, t_step, tabs: DeviceTables, clip, sigma_mode, out=None, t_dev=None):
+    L.require_device(x_t)
+    _chk(x_t, f32)
+    _chk(model_out, f32)
+    out = torch.empty_like(x_t) if out is None else out
+    p = L.PSampleParams()
+    p.x_t, p.model_out, p.z, p.x_prev = L.ptr(x_t), L.ptr(model_out), L.ptr(z), L.ptr(out)
+    p.tab = tabs.struct()
+    p.t_step_dev = L.ptr(t_dev)
+    p.t_step = int(t_step) if t_dev is None else 1
+    B, Cc = x_t.shape[0], x_t.shape[1]
+    p.B, p.C, p.c_out, p.hw = B, Cc, model_out.shape[1], x_t.numel() // (B * Cc)
+    p.clip, p.sigma_mode = 1 if clip else 0, SIGMA_MODES[sigma_mode]
+    L.call("pddm_p_sample_step", C.byref(p), L.stream())
+    return out
+
+
+def vlb_terms(x0, x_t, model_out, t, tabs: DeviceTables, mode, sigma_mode="beta", want_grad_v=False):
+    L.require_device(x0)
+    _chk(x0, f32)
+    B, Cc = x0.shape[0], x0.shape[1]
+    out = torch.empty(B, dtype=f32, device=x0.device)
+    gv = torch.empty_like(x0) if want_grad_v else None
+    p = L.VlbParams()
+    p.x0, p.out, p.grad_v = L.ptr(x0), L.ptr(out), L.ptr(gv)
+    if mode != 2:
+        t = t.to(device=x0.device, dtype=torch.int64).contiguous()
+        p.x_t, p.model_out, p.t = L.ptr(_chk(x_t, f32)), L.ptr(_chk(model_out, f32)), L.ptr(t)
+        p.c_out = model_out.shape[1]
+    p.tab = tabs.struct()
+    p.B, p.C, p.hw, p.mode = B, Cc, x0.numel() // (B * Cc), mode
+    p.sigma_mode = SIGMA_MODES[sigma_mode] if sigma_mode in SIGMA_MODES else 0
+    L.call("pddm_vlb_terms", C.byref(p), L.stream())
+    return out, gv
+
+
+def step_advance(t_dev, t_vec):
+    L.call("pddm_step_advance", L.ptr(t_dev), L.ptr(t_vec), t_vec.shape[0], L.stream())
+
+
+def adam_ema_step(param, grad, exp_avg, exp_avg_sq, ema, lr, beta1, beta2, eps, weight_decay, ema_decay, step,
+                  grad_scale=1.0, step_dev=None, lr_dev=None):
+    p = L.AdamParams()
+    p.param, p.grad, p.exp_avg, p.exp_avg_sq, p.ema = L.ptr(param), L.ptr(grad), L.ptr(exp_avg), L.ptr(exp_avg_sq), L.ptr(ema)
+    p.n = param.numel()
+    p.lr, p.beta1, p.beta2, p.eps, p.weight_decay = lr, beta1, beta2, eps, weight_decay
+    p.ema_decay, p.grad_scale, p.step = (ema_decay if ema_decay is not None else 0.0), grad_scale, step
+    p.step_dev, p.lr_dev = L.ptr(step_dev), L.ptr(lr_dev)
+    L.call("pddm_adam_ema_step", C.byref(p), L.stream())

@@ -1,0 +1,489 @@
+"""torch.library registration of the sm_100a kernels (namespace ``pddm``) with fake (shape) and autograd rules.
+
+Each forward op has a matching ``*_bwd`` op; ``register_autograd`` wires them together, so the ops compose
+under ``loss.backward()``, ``torch.no_grad()`` and CUDA-graph capture.  Tensors inside the network are
+contiguous NHWC bf16; the ops never fall back to eager torch math -- on a non-sm_100 device they raise.
+
+Weight operands: parameters stay fp32 ``nn.Parameter``s with the reference's names/shapes; the bf16 GEMM packs
+are produced by ``pddm_pack_conv_weight``.  While training they are re-packed on every call (weights change
+each step; ~0.1 ms per step for 49 M parameters).  Inside ``frozen_weights()`` (sampling / evaluation) packs
+are cached per parameter version.
+"""
+import contextlib
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import functional as F
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+_FROZEN = [0]
+_EPOCH = [0]
+_PACK_CACHE = {}
+
+
+@contextlib.contextmanager
+def frozen_weights():
+    """Parameters are not going to change inside this block: reuse cached bf16 weight packs."""
+    _FROZEN[0] += 1
+    try:
+        yield
+    finally:
+        _FROZEN[0] -= 1
+
+
+def invalidate_weight_cache():
+    _EPOCH[0] += 1
+    _PACK_CACHE.clear()
+
+
+def _packed(w, mode):
+    if not _FROZEN[0]:
+        return F.pack_weight(w, mode)
+    key = (w.data_ptr(), mode)
+    ent = _PACK_CACHE.get(key)
+    stamp = (w._version, _EPOCH[0], tuple(w.shape))
+    if ent is None or ent[0] != stamp:
+        ent = (stamp, F.pack_weight(w, mode))
+        _PACK_CACHE[key] = ent
+    return ent[1]
+
+
+def _empty(like):
+    return torch.empty(0, dtype=f32, device=like.device)
+
+
+def _opt(t):
+    return None if (t is None or t.numel() == 0) else t
+
+
+# ================================================================================================ conv2d
+@torch.library.custom_op("pddm::conv2d", mutates_args=())
+def conv2d(x: Tensor, weight: Tensor, bias: Optional[Tensor], bcast: Optional[Tensor], residual: Optional[Tensor],
+           stride: int, upsample: bool) -> Tuple[Tensor, Tensor]:
+    """NHWC bf16 conv (3x3 pad 1 | 1x1), optional nearest-x2 upsample in front, stride 1|2, fused epilogue
+    ``+ bias[n] + bcast[b, n] + residual``.  Returns (y, x_gemm) where x_gemm is the tensor the GEMM actually read
+    (upsampled / phase-split copy) or an empty placeholder when that is ``x`` itself."""
+    B, H, W, Cin = x.shape
+    k = weight.shape[-1] if weight.dim() == 4 else 1
+    wp = _packed(weight, 0)
+    xin = x
+    aux = _empty(x)
+    if upsample:
+        xin = aux = F.upsample2x(x)
+        H, W = 2 * H, 2 * W
+    if stride == 2:
+        assert k == 3 and H % 2 == 0 and W % 2 == 0
+        xin = aux = F.phase_split(xin)
+        H, W = H // 2, W // 2
+        taps = F.taps_stride2(B)
+    else:
+        taps = F.taps_3x3() if k == 3 else F.taps_1x1()
+    y = F.tap_gemm(xin, wp, taps, B, H, W, bias=bias, bcast=bcast, residual=residual)
+    return y, aux
+
+
+@conv2d.register_fake
+def _(x, weight, bias, bcast, residual, stride, upsample):
+    B, H, W, _ = x.shape
+    if upsample:
+        H, W = 2 * H, 2 * W
+    aux = x.new_empty((0,), dtype=f32)
+    if stride == 2:
+        aux = x.new_empty((4 * B, H // 2, W // 2, x.shape[-1]))
+        H, W = H // 2, W // 2
+    elif upsample:
+        aux = x.new_empty((B, H, W, x.shape[-1]))
+    return x.new_empty((B, H, W, weight.shape[0])), aux
+
+
+@torch.library.custom_op("pddm::conv2d_bwd", mutates_args=())
+def conv2d_bwd(dy: Tensor, xin: Tensor, weight: Tensor, stride: int, upsample: bool, in_h: int, in_w: int,
+               need_dx: bool, need_dbias: bool, need_dbcast: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """-> (dx, dweight, dbias, dbcast); unused outputs are empty placeholders.  xin = tensor the forward GEMM read."""
+    B, H, W, Cout = dy.shape  # tile space of the forward GEMM
+    Cin = weight.shape[1]
+    k = weight.shape[-1] if weight.dim() == 4 else 1
+    if stride == 2:
+        taps = F.taps_stride2(B)
+    else:
+        taps = F.taps_3x3() if k == 3 else F.taps_1x1()
+    dw = F.tap_wgrad(xin, dy, taps, B, H, W, Cin, Cout, tuple(weight.shape))
+    dbias = F.colsum(dy, Cout) if need_dbias else _empty(dy)
+    dbcast = F.colsum_per_sample(dy) if need_dbcast else _empty(dy)
+    dx = _empty(dy)
+    if need_dx:
+        wp1 = _packed(weight, 1)  # [Cin, taps(flipped), Cout]
+        if stride == 2:
+            dx = torch.empty((B, 2 * H, 2 * W, Cin), dtype=bf16, device=dy.device)
+            for a in range(2):
+                for b in range(2):
+                    F.tap_gemm(dy, wp1, F.taps_stride2_dgrad(a, b), B, H, W, out=dx, out_hw=(2 * H, 2 * W),
+                               out_map=(2, 2, a, b))
+        else:
+            dx = F.tap_gemm(dy, wp1, taps, B, H, W)
+        if upsample:
+            dx = F.upsample2x_bwd(dx)
+    return dx, dw, dbias, dbcast
+
+
+@conv2d_bwd.register_fake
+def _(dy, xin, weight, stride, upsample, in_h, in_w, need_dx, need_dbias, need_dbcast):
+    B = dy.shape[0]
+    e = dy.new_empty((0,), dtype=f32)
+    dx = dy.new_empty((B, in_h, in_w, weight.shape[1])) if need_dx else e
+    return (dx, weight.new_empty(weight.shape), dy.new_empty((dy.shape[-1],), dtype=f32) if need_dbias else e,
+            dy.new_empty((B, dy.shape[-1]), dtype=f32) if need_dbcast else e)
+
+
+def _conv_setup(ctx, inputs, output):
+    x, weight, bias, bcast, residual, stride, upsample = inputs
+    _, aux = output
+    ctx.save_for_backward(x if aux.numel() == 0 else aux, weight)
+    ctx.meta = (stride, upsample, x.shape[1], x.shape[2])
+    ctx.needs = (x.requires_grad, bias is not None and bias.requires_grad, bcast is not None and bcast.requires_grad,
+                 residual is not None and residual.requires_grad)
+
+
+def _conv_backward(ctx, dy, _daux):
+    xin, weight = ctx.saved_tensors
+    stride, upsample, in_h, in_w = ctx.meta
+    need_dx, need_db, need_dbc, need_dres = ctx.needs
+    dy = dy.contiguous()
+    dx, dw, db, dbc = torch.ops.pddm.conv2d_bwd(dy, xin, weight, stride, upsample, in_h, in_w, need_dx, need_db, need_dbc)
+    return (dx if need_dx else None, dw, db if need_db else None, dbc if need_dbc else None,
+            dy if need_dres else None, None, None)
+
+
+torch.library.register_autograd("pddm::conv2d", _conv_backward, setup_context=_conv_setup)
+
+
+# ================================================================================================ linear
+@torch.library.custom_op("pddm::linear", mutates_args=())
+def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
+    """[M, K] bf16 @ weight[N, K]^T + bias -> fp32 [M, N]  (src/modules/nn.py:36-40), tcgen05 tap-GEMM with one tap."""
+    M, K = x.shape
+    wp = _packed(weight.view(weight.shape[0], K, 1), 0)
+    y = F.tap_gemm(x.view(1, 1, M, K), wp, F.taps_1x1(), 1, 1, M, bias=bias, out_dtype=f32)
+    return y.view(M, weight.shape[0])
+
+
+@linear.register_fake
+def _(x, weight, bias):
+    return x.new_empty((x.shape[0], weight.shape[0]), dtype=f32)
+
+
+@torch.library.custom_op("pddm::linear_bwd", mutates_args=())
+def linear_bwd(dy: Tensor, x: Tensor, weight: Tensor, need_dx: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """dy fp32 [M, N] -> (dx fp32 [M, K], dweight, dbias)."""
+    M, N = dy.shape
+    K = x.shape[1]
+    dyb = F.convert(dy, bf16)
+    dw = F.tap_wgrad(x.view(1, 1, M, K), dyb.view(1, 1, M, N), F.taps_1x1(), 1, 1, M, K, N, (N, K, 1)).view(N, K)
+    db = F.colsum(dyb, N)
+    dx = _empty(dy)
+    if need_dx:
+        wp1 = _packed(weight.view(N, K, 1), 1)
+        dx = F.tap_gemm(dyb.view(1, 1, M, N), wp1, F.taps_1x1(), 1, 1, M, out_dtype=f32).view(M, K)
+    return dx, dw, db
+
+
+@linear_bwd.register_fake
+def _(dy, x, weight, need_dx):
+    return (dy.new_empty(x.shape, dtype=f32) if need_dx else dy.new_empty((0,)), weight.new_empty(weight.shape),
+            dy.new_empty((weight.shape[0],)))
+
+
+def _lin_setup(ctx, inputs, output):
+    x, weight, bias = inputs
+    ctx.save_for_backward(x, weight)
+    ctx.need_dx = x.requires_grad
+    ctx.has_bias = bias is not None
+
+
+def _lin_backward(ctx, dy):
+    x, weight = ctx.saved_tensors
+    dx, dw, db = torch.ops.pddm.linear_bwd(dy.contiguous(), x, weight, ctx.need_dx)
+    return (dx if ctx.need_dx else None), dw, (db if ctx.has_bias else None)
+
+
+torch.library.register_autograd("pddm::linear", _lin_backward, setup_context=_lin_setup)
+
+
+# ================================================================================================ silu / cast on vectors
+@torch.library.custom_op("pddm::silu_vec", mutates_args=())
+def silu_vec(x: Tensor) -> Tensor:
+    """fp32 [.., N] -> bf16 SiLU (the emb_layers / time_embed activations, src/modules/unet.py:151-157,340-345)."""
+    return F.silu_vec(x, bf16)
+
+
+@silu_vec.register_fake
+def _(x):
+    return x.new_empty(x.shape, dtype=bf16)
+
+
+@torch.library.custom_op("pddm::silu_vec_bwd", mutates_args=())
+def silu_vec_bwd(x: Tensor, dy: Tensor) -> Tensor:
+    return F.silu_vec_bwd(x, F.convert(dy.contiguous(), f32))
+
+
+@silu_vec_bwd.register_fake
+def _(x, dy):
+    return x.new_empty(x.shape)
+
+
+torch.library.register_autograd(
+    "pddm::silu_vec", lambda ctx, dy: torch.ops.pddm.silu_vec_bwd(ctx.saved_tensors[0], dy),
+    setup_context=lambda ctx, inputs, output: ctx.save_for_backward(inputs[0]))
+
+
+@torch.library.custom_op("pddm::cast_bf16", mutates_args=())
+def cast_bf16(x: Tensor) -> Tensor:
+    return F.convert(x, bf16) if x.dtype != bf16 else x.clone()
+
+
+@cast_bf16.register_fake
+def _(x):
+    return x.new_empty(x.shape, dtype=bf16)
+
+
+@torch.library.custom_op("pddm::cast_f32", mutates_args=())
+def cast_f32(x: Tensor) -> Tensor:
+    return F.convert(x, f32) if x.dtype != f32 else x.clone()
+
+
+@cast_f32.register_fake
+def _(x):
+    return x.new_empty(x.shape, dtype=f32)
+
+
+torch.library.register_autograd("pddm::cast_bf16", lambda ctx, g: torch.ops.pddm.cast_f32(g.contiguous()))
+torch.library.register_autograd("pddm::cast_f32", lambda ctx, g: torch.ops.pddm.cast_bf16(g.contiguous()))
+
+
+@torch.library.custom_op("pddm::timestep_embedding", mutates_args=())
+def timestep_embedding(t: Tensor, dim: int, max_period: float) -> Tensor:
+    """src/modules/nn.py:104-122 -> bf16 [B, dim]."""
+    return F.timestep_embedding(t, dim, max_period, bf16)
+
+
+@timestep_embedding.register_fake
+def _(t, dim, max_period):
+    return t.new_empty((t.shape[0], dim), dtype=bf16)
+
+
+# ================================================================================================ group norm (+SiLU)
+@torch.library.custom_op("pddm::gn_silu", mutates_args=())
+def gn_silu(x: Tensor, gamma: Tensor, beta: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], groups: int,
+            eps: float, silu: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """GroupNorm32 (+scale-shift) (+SiLU) on NHWC (src/modules/nn.py:13-20,94-101) -> (y bf16, mean, rstd)."""
+    return F.gn_silu_fwd(x, gamma, beta, groups, eps, silu, scale, shift)
+
+
+@gn_silu.register_fake
+def _(x, gamma, beta, scale, shift, groups, eps, silu):
+    return x.new_empty(x.shape, dtype=bf16), x.new_empty((x.shape[0], groups), dtype=f32), \
+        x.new_empty((x.shape[0], groups), dtype=f32)
+
+
+@torch.library.custom_op("pddm::gn_silu_bwd", mutates_args=())
+def gn_silu_bwd(x: Tensor, dy: Tensor, gamma: Tensor, beta: Tensor, scale: Optional[Tensor], shift: Optional[Tensor],
+                mean: Tensor, rstd: Tensor, groups: int, silu: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    dx, dg, db, _, dsc, dsh = F.gn_silu_bwd(x, dy, gamma, beta, mean, rstd, groups, silu, scale, shift, dx_dtype=x.dtype)
+    return dx, dg, db, dsc if dsc is not None else _empty(x), dsh if dsh is not None else _empty(x)
+
+
+@gn_silu_bwd.register_fake
+def _(x, dy, gamma, beta, scale, shift, mean, rstd, groups, silu):
+    e = x.new_empty((0,), dtype=f32)
+    ss = x.new_empty(scale.shape, dtype=f32) if scale is not None else e
+    return x.new_empty(x.shape), gamma.new_empty(gamma.shape), gamma.new_empty(gamma.shape), ss, ss
+
+
+def _gn_setup(ctx, inputs, output):
+    x, gamma, beta, scale, shift, groups, eps, silu = inputs
+    _, mean, rstd = output
+    ctx.save_for_backward(x, gamma, beta, mean, rstd, *([scale, shift] if scale is not None else []))
+    ctx.meta = (groups, silu, scale is not None)
+
+
+def _gn_backward(ctx, dy, _dm, _dr):
+    groups, silu, has_ss = ctx.meta
+    if has_ss:
+        x, gamma, beta, mean, rstd, scale, shift = ctx.saved_tensors
+    else:
+        x, gamma, beta, mean, rstd = ctx.saved_tensors
+        scale = shift = None
+    dx, dg, db, dsc, dsh = torch.ops.pddm.gn_silu_bwd(x, dy.contiguous(), gamma, beta, scale, shift, mean, rstd, groups, silu)
+    return dx, dg, db, (dsc if has_ss else None), (dsh if has_ss else None), None, None, None
+
+
+torch.library.register_autograd("pddm::gn_silu", _gn_backward, setup_context=_gn_setup)
+
+
+# ================================================================================================ attention
+@torch.library.custom_op("pddm::attention", mutates_args=())
+def attention(qkv: Tensor, heads: int) -> Tuple[Tensor, Tensor]:
+    """QKVAttention (src/modules/unet.py:237-256) on bf16 [B, T, 3C] -> (out [B, T, C], lse [B, heads, T])."""
+    return F.attn_fwd(qkv, heads)
+
+
+@attention.register_fake
+def _(qkv, heads):
+    B, T, C3 = qkv.shape
+    return qkv.new_empty((B, T, C3 // 3)), qkv.new_empty((B, heads, T), dtype=f32)
+
+
+@torch.library.custom_op("pddm::attention_bwd", mutates_args=())
+def attention_bwd(qkv: Tensor, out: Tensor, dout: Tensor, lse: Tensor, heads: int) -> Tensor:
+    return F.attn_bwd(qkv, out, dout, lse, heads)
+
+
+@attention_bwd.register_fake
+def _(qkv, out, dout, lse, heads):
+    return qkv.new_empty(qkv.shape)
+
+
+def _attn_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0], output[0], output[1])
+    ctx.heads = inputs[1]
+
+
+def _attn_backward(ctx, dout, _dlse):
+    qkv, out, lse = ctx.saved_tensors
+    return torch.ops.pddm.attention_bwd(qkv, out, dout.contiguous(), lse, ctx.heads), None
+
+
+torch.library.register_autograd("pddm::attention", _attn_backward, setup_context=_attn_setup)
+
+
+# ================================================================================================ concat / add
+@torch.library.custom_op("pddm::concat_channels", mutates_args=())
+def concat_channels(a: Tensor, b: Tensor) -> Tensor:
+    """th.cat([h, skip], dim=1) on NHWC bf16 (src/modules/unet.py:492)."""
+    return F.concat_channels(a, b)
+
+
+@concat_channels.register_fake
+def _(a, b):
+    return a.new_empty(a.shape[:-1] + (a.shape[-1] + b.shape[-1],))
+
+
+@torch.library.custom_op("pddm::split_channels", mutates_args=())
+def split_channels(x: Tensor, c1: int) -> Tuple[Tensor, Tensor]:
+    return F.split_channels(x, c1)
+
+
+@split_channels.register_fake
+def _(x, c1):
+    return x.new_empty(x.shape[:-1] + (c1,)), x.new_empty(x.shape[:-1] + (x.shape[-1] - c1,))
+
+
+torch.library.register_autograd(
+    "pddm::concat_channels", lambda ctx, g: tuple(torch.ops.pddm.split_channels(g.contiguous(), ctx.c1)),
+    setup_context=lambda ctx, inputs, output: setattr(ctx, "c1", inputs[0].shape[-1]))
+
+
+@torch.library.custom_op("pddm::add", mutates_args=())
+def add(a: Tensor, b: Tensor) -> Tensor:
+    """bf16 elementwise add (gradient fan-in of tensors that feed two consumers)."""
+    return F.add_bf16(a, b)
+
+
+@add.register_fake
+def _(a, b):
+    return a.new_empty(a.shape)
+
+
+torch.library.register_autograd("pddm::add", lambda ctx, g: (g, g))
+
+
+# ================================================================================================ stem / head
+@torch.library.custom_op("pddm::stem_conv", mutates_args=())
+def stem_conv(x: Tensor, weight: Tensor, bias: Tensor) -> Tensor:
+    """First conv (Cin <= 4): NCHW fp32 model input -> NHWC bf16 (src/modules/unet.py:353)."""
+    return F.stem_conv_fwd(x, weight, bias)
+
+
+@stem_conv.register_fake
+def _(x, weight, bias):
+    return x.new_empty((x.shape[0], x.shape[2], x.shape[3], weight.shape[0]), dtype=bf16)
+
+
+@torch.library.custom_op("pddm::stem_conv_bwd", mutates_args=())
+def stem_conv_bwd(x: Tensor, dy: Tensor, weight: Tensor) -> Tuple[Tensor, Tensor]:
+    return F.stem_conv_wgrad(x, dy, tuple(weight.shape))
+
+
+@stem_conv_bwd.register_fake
+def _(x, dy, weight):
+    return weight.new_empty(weight.shape), weight.new_empty((weight.shape[0],))
+
+
+def _stem_backward(ctx, dy):
+    x, w = ctx.saved_tensors
+    dw, db = torch.ops.pddm.stem_conv_bwd(x, dy.contiguous(), w)
+    return None, dw, db  # the model input needs no gradient (x_t is data)
+
+
+torch.library.register_autograd("pddm::stem_conv", _stem_backward,
+                                setup_context=lambda ctx, inputs, output: ctx.save_for_backward(inputs[0], inputs[1]))
+
+
+@torch.library.custom_op("pddm::head_conv", mutates_args=())
+def head_conv(x: Tensor, weight: Tensor, bias: Tensor) -> Tensor:
+    """Last conv (Cout <= 8): NHWC bf16 -> NCHW fp32 model output (src/modules/unet.py:440)."""
+    return F.head_conv_fwd(x, weight, bias)
+
+
+@head_conv.register_fake
+def _(x, weight, bias):
+    return x.new_empty((x.shape[0], weight.shape[0], x.shape[1], x.shape[2]), dtype=f32)
+
+
+@torch.library.custom_op("pddm::head_conv_bwd", mutates_args=())
+def head_conv_bwd(x: Tensor, weight: Tensor, dy: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    return F.head_conv_bwd(x, weight, dy)
+
+
+@head_conv_bwd.register_fake
+def _(x, weight, dy):
+    return x.new_empty(x.shape), weight.new_empty(weight.shape), weight.new_empty((weight.shape[0],))
+
+
+def _head_backward(ctx, dy):
+    x, w = ctx.saved_tensors
+    return tuple(torch.ops.pddm.head_conv_bwd(x, w, dy.contiguous()))
+
+
+torch.library.register_autograd("pddm::head_conv", _head_backward,
+                                setup_context=lambda ctx, inputs, output: ctx.save_for_backward(inputs[0], inputs[1]))
+
+
+# ================================================================================================ layout at the seam
+@torch.library.custom_op("pddm::to_nhwc", mutates_args=())
+def to_nhwc(x: Tensor) -> Tensor:
+    """NCHW fp32 -> NHWC bf16."""
+    return F.nchw_to_nhwc(x.contiguous(), bf16)
+
+
+@to_nhwc.register_fake
+def _(x):
+    return x.new_empty((x.shape[0], x.shape[2], x.shape[3], x.shape[1]), dtype=bf16)
+
+
+@torch.library.custom_op("pddm::to_nchw", mutates_args=())
+def to_nchw(x: Tensor) -> Tensor:
+    """NHWC bf16/fp32 -> NCHW fp32."""
+    return F.nhwc_to_nchw(x.contiguous())
+
+
+@to_nchw.register_fake
+def _(x):
+    return x.new_empty((x.shape[0], x.shape[3], x.shape[1], x.shape[2]), dtype=f32)
+
+
+torch.library.register_autograd("pddm::to_nhwc", lambda ctx, g: torch.ops.pddm.to_nchw(g))
+torch.library.register_autograd("pddm::to_nchw", lambda ctx, g: torch.ops.pddm.to_nhwc(g))

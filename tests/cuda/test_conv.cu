@@ -112,7 +112,8 @@ static int run_case(const Case& c) {
   p.y_dtype = c.y_dtype;
   p.x_NB = c.x_NB; p.B = c.B; p.H = c.H; p.W = c.W; p.Cin = c.Cin; p.ldx = c.ldx; p.Cout = c.Cout;
   p.ntaps = c.ntaps;
-  for (int t = 0; t < c.ntaps; ++t) { p.tap_db[t] = c.db[t]; p.tap_dh[t] = c.dh[t]; p.tap_dw[t] = c.dw[t]; }
+  for (int t = 0; t < c.ntaps; ++t) { p.tap_db[t] = c.db[t]; p.tap_dh[t] = c.dh[t]; p.tap_dw[t] = c.dw[t]; p.tap_w[t] = t; }
+  p.w_ntaps = c.ntaps;
   p.out_H = c.out_H; p.out_W = c.out_W; p.out_sh = c.sh; p.out_sw = c.sw; p.out_oh = c.oh; p.out_ow = c.ow;
   int rc = pddm_conv2d_fwd(&p, nullptr);
   cudaError_t e = cudaDeviceSynchronize();

@@ -1,0 +1,110 @@
+"""GPU parity of the whole UNet (forward + gradients) against the CPU oracle with identical parameters, and
+against the fixtures recorded from the reference.  The network computes in bf16 with fp32 accumulation; the
+oracle is fp32, so tolerances are relative L2 errors (stated per check)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.gen_golden import TINY, synth_batch
+from oracle.unet_ref import MODEL_CONFIGS, arch_from_config, make_params, unet_forward
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def build(cfg, res, seed, learn_sigma=False):
+    from probabilisticdeepdiffusionmodels_b200.modules import get_unet
+    kw = {k: v for k, v in cfg.items() if k != "name"}
+    arch = arch_from_config(res, **kw, learn_sigma=learn_sigma)
+    m = get_unet(res, **kw, learn_sigma=learn_sigma)
+    P = make_params(arch, seed=seed)
+    m.load_state_dict(P)
+    return m.cuda(), arch, P
+
+
+CASES = [("tiny", TINY, 16, False), ("tiny_ss", dict(TINY, use_scale_shift_norm=True), 16, False),
+         ("tiny_sigma", TINY, 16, True), ("small_grey28", MODEL_CONFIGS["unet_small_grey"], 28, False),
+         ("small_grey32", MODEL_CONFIGS["unet_small_grey"], 32, False)]
+
+
+@pytest.mark.parametrize("tag,cfg,res,ls", CASES)
+def test_unet_matches_reference_fixture(golden, tag, cfg, res, ls):
+    g = golden["unet"]
+    m, arch, P = build(cfg, res, 11, ls)
+    _, t, noise = synth_batch(3, 2, cfg["in_channels"], res, 1000)
+    y = m(noise.cuda(), t.cuda())
+    assert y.dtype == torch.float32 and tuple(y.shape) == tuple(g[f"{tag}_y"].shape)
+    # bf16 activations through ~20-60 layers vs the fp32 reference: relative L2 error bound 1.5e-2
+    assert rel(y, g[f"{tag}_y"]) < 1.5e-2
+    y2 = m(noise.cuda(), t.float().cuda())  # sampling passes float32 timesteps (src/engine.py:386)
+    assert rel(y2, g[f"{tag}_y_float_t"]) < 1.5e-2
+    gy = torch.from_numpy(np.random.RandomState(5).standard_normal(tuple(y.shape)).astype(np.float32)).cuda()
+    m.zero_grad()
+    (m(noise.cuda(), t.cuda()) * gy).sum().backward()
+    names = list(g[f"{tag}_grad_names"])
+    got = dict(m.named_parameters())
+    norms_ref = g[f"{tag}_grad_norms"]
+    bad = {}
+    for n, nr in zip(names, norms_ref):
+        assert got[n].grad is not None, n
+        if nr > 1e-3:  # skip mathematically-zero gradients (biases in front of a 1-channel-per-group GN)
+            e = abs(float(got[n].grad.double().norm()) - nr) / nr
+            if e > 5e-2:
+                bad[n] = round(e, 4)
+    assert not bad, bad
+    for key in g.files:
+        if key.startswith(f"{tag}_grad::"):
+            n = key.split("::")[1]
+            if float(np.linalg.norm(g[key])) < 1e-3:
+                continue  # mathematically zero (bias in front of a 1-channel-per-group GN): pure rounding noise
+            assert rel(got[n].grad, g[key]) < 5e-2, n
+
+
+def test_unet_cifar_config_forward_backward():
+    """BASELINE config 2 architecture at B=4 against the oracle run on CPU here."""
+    cfg = MODEL_CONFIGS["unet"]
+    m, arch, P = build(cfg, 32, 5)
+    _, t, noise = synth_batch(7, 4, 3, 32, 1000)
+    t[0], t[1] = 1, 1000
+    Pr = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    yr = unet_forward(Pr, arch, noise, t)
+    gy = torch.from_numpy(np.random.RandomState(6).standard_normal(tuple(yr.shape)).astype(np.float32))
+    (yr * gy).sum().backward()
+    y = m(noise.cuda(), t.cuda())
+    (y * gy.cuda()).sum().backward()
+    e = rel(y, yr.detach())
+    assert e < 2e-2, e
+    got = dict(m.named_parameters())
+    errs = {n: rel(got[n].grad, Pr[n].grad) for n in Pr if float(Pr[n].grad.norm()) > 1e-3}
+    bad = {n: v for n, v in errs.items() if v > 8e-2}
+    assert not bad, bad
+
+
+def test_no_grad_and_frozen_weight_cache():
+    from probabilisticdeepdiffusionmodels_b200.ops import frozen_weights
+    cfg = MODEL_CONFIGS["unet_small_grey"]
+    m, arch, P = build(cfg, 28, 21)
+    _, t, noise = synth_batch(9, 3, 1, 28, 1000)
+    with torch.no_grad():
+        y0 = m(noise.cuda(), t.cuda())
+        with frozen_weights():
+            y1 = m(noise.cuda(), t.cuda())
+            y2 = m(noise.cuda(), t.cuda())
+    assert torch.equal(y0, y1) and torch.equal(y1, y2)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(0.01)
+        with frozen_weights():
+            y3 = m(noise.cuda(), t.cuda())  # in-place update bumps the version -> packs refreshed
+    assert not torch.equal(y3, y1)
+
+
+def test_cpu_input_raises():
+    from probabilisticdeepdiffusionmodels_b200.modules import get_model
+    m = get_model(28, dict(MODEL_CONFIGS["unet_small_grey"]))
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 1, 28, 28), torch.ones(1))
