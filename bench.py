@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path on BASELINE.json's metric: train img/s (+ 1000-step samples/s) of the CIFAR-10-shape
+improved-diffusion UNet (config/model/unet.yaml, cosine schedule, learned variance, L_hybrid, bf16 compute).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One "step" = one optimisation step (q_sample, UNet forward, L_hybrid, backward, Adam) on 128 synthetic images per
+GPU (weak scaling; the gradient all-reduce is part of the step for N > 1).  The timed region replays the captured
+CUDA graph K times between CUDA events; rank 0 prints ONE JSON line.  ``--impl reference`` times the CPU oracle
+port of the reference's own PyTorch path (oracle/) on the host cores for the same metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "train img/s (+ 1000-step samples/s), CIFAR-10 32x32 improved-diffusion UNet"
+MODEL = "unet"
+RES = 32
+PER_GPU_BATCH = 128
+CPU_BATCH = 16
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p["bf16_tflops"], p.get("bf16_tflops_sustained", p["bf16_tflops"]), p["hbm_gbs"], "measured"
+    except Exception:
+        return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_arm(steps, warmup, batch=CPU_BATCH, threads=None):
+    """The reference's own PyTorch path (CPU oracle port, fp32): training step with Adam + a few reverse steps."""
+    import numpy as np
+    import torch
+
+    from oracle import engine_ref as E
+    from oracle.diffusion_ref import DiffusionRef
+    from oracle.unet_ref import MODEL_CONFIGS, arch_from_config, make_params
+
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    cfg = MODEL_CONFIGS[MODEL]
+    arch = arch_from_config(RES, **{k: v for k, v in cfg.items() if k != "name"}, learn_sigma=True)
+    P = {k: v.requires_grad_(True) for k, v in make_params(arch, seed=1).items()}
+    diff = DiffusionRef(1000, mode="cosine")
+    opt = torch.optim.Adam(list(P.values()), lr=1e-4)
+    g = torch.Generator().manual_seed(0)
+    x0 = torch.rand((batch, 3, RES, RES), generator=g) * 2 - 1
+
+    def step():
+        t = torch.randint(1, 1001, (batch,), generator=g)
+        noise = torch.randn(x0.shape, generator=g)
+        opt.zero_grad(set_to_none=True)
+        loss, _ = E.train_loss(P, arch, diff, x0, t, noise, learn_sigma=True)
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    # sampling: a few reverse steps, extrapolated to 1000-step chains (stated in `sample`)
+    xs = torch.randn((batch, 3, RES, RES), generator=g)
+    nst = 3
+    with torch.no_grad():
+        E.denoising_step(P, arch, diff, xs, 1000, torch.randn(xs.shape, generator=g), True, learn_sigma=True)
+        t1 = time.perf_counter()
+        for k in range(nst):
+            xs = E.denoising_step(P, arch, diff, xs, 999 - k, torch.randn(xs.shape, generator=g), True,
+                                  learn_sigma=True)
+        ds = (time.perf_counter() - t1) / nst
+    return {"train_img_s": batch / dt, "ms_per_step": dt * 1e3, "image_steps_s": batch / ds,
+            "samples_s": batch / ds / 1000.0, "cores": threads, "batch": batch,
+            "sample": f"{steps} timed train steps (+{warmup} warm-up) at B={batch} fp32 on {threads} host threads; "
+                      f"sampling = {nst} reverse steps at B={batch} extrapolated x1000/{nst} to 1000-step chains"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--sample-steps", type=int, default=1000, help="length of the timed reverse chain")
+    ap.add_argument("--no-sampling", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    cfg_json = {"workload": "BASELINE configs[1]: CIFAR-10-shape 3x32x32 UNet (config/model/unet.yaml), cosine "
+                            "schedule, learned variance, L_hybrid, Adam, bf16 compute / fp32 accumulate",
+                "per_gpu_batch": args.batch, "global_batch": args.batch * max(world, 1), "parallelism": f"dp{world}",
+                "l2_policy": "activations + weights + grads per step (>2 GB) exceed the 126 MB L2; no explicit flush"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 5))
+        warm = max(1, min(args.warmup, 1))
+        r = cpu_reference_arm(steps, warm)
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": r["train_img_s"], "unit": "img/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg_json,
+            "sampling": {"value": r["samples_s"], "unit": "samples/s (1000-step chains)",
+                         "image_steps_per_s": r["image_steps_s"]},
+            "cpu_baseline": {"value": r["train_img_s"], "unit": "img/s", "cores": r["cores"], "kind": "port",
+                             "sample": r["sample"]},
+            "e2e": {"value": r["train_img_s"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from oracle.unet_ref import MODEL_CONFIGS, arch_from_config, fwd_flops_per_image, make_params
+    from probabilisticdeepdiffusionmodels_b200 import Engine, _lib, parallel
+
+    rank, world, local_rank = parallel.init_from_env("nccl")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    cfg = MODEL_CONFIGS[MODEL]
+    arch = arch_from_config(RES, **{k: v for k, v in cfg.items() if k != "name"}, learn_sigma=True)
+    eng = Engine(dict(cfg), {"lr": 1e-4}, diffusion_steps=1000, mode="cosine", resolution=RES,
+                 clip_while_generating=True, learn_sigma=True, log_loss_per_t=False)
+    eng.model.load_state_dict(make_params(arch, seed=1))  # random init incl. the reference's zero-init convs
+    eng = eng.to(dev)
+    parallel.broadcast_parameters(eng.model)
+    B = args.batch
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_x = (torch.rand((B, 3, RES, RES), generator=g) * 2 - 1).pin_memory()
+    x_dev = host_x.to(dev)
+    hook = parallel.FlatGradAllReduce() if world > 1 else None
+
+    launches0 = _lib.KERNELS[0]
+    step = eng.capture_train_step((B, 3, RES, RES), grad_hook=hook)
+    # capture_train_step ran 3 eager warm-ups + 1 capture: kernels per step = delta / 4
+    kernels_per_step = (_lib.KERNELS[0] - launches0) // 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step(x_dev)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            eng._train_graph["graph"].replay()
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+
+    # end-to-end through the public step(x): pinned host batch -> device each step, loss read back each step
+    for _ in range(2):
+        float(step(host_x))
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        loss_val = float(step(host_x))  # H2D copy (non_blocking, pinned) + graph replay + D2H of the loss (sync)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+    _ = t0
+
+    t_ms = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t_ms[0]), float(t_ms[1])
+    img_s = B * world / (ms * 1e-3)
+    img_s_e2e = B * world / (ms_e2e * 1e-3)
+
+    # ---- sampling: one full reverse chain per GPU (batch-sharded, no collective)
+    sampling = None
+    if not args.no_sampling:
+        gen = torch.Generator(device=dev).manual_seed(99 + rank)
+        xT = torch.randn((B, 3, RES, RES), generator=gen, device=dev)
+        with torch.no_grad():
+            eng.sample_from_step(xT, 5, generator=gen)  # warm-up + graph capture
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            out = eng.sample_from_step(xT, args.sample_steps, generator=gen)
+            s1.record()
+            barrier()
+        chain_ms = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(chain_ms, op=dist.ReduceOp.MAX)
+        chain_s = float(chain_ms[0]) * 1e-3
+        steps_s = B * world * args.sample_steps / chain_s
+        sampling = {"value": steps_s / 1000.0, "unit": "samples/s (1000-step chains)", "image_steps_per_s": steps_s,
+                    "chain_steps_timed": args.sample_steps, "chain_seconds": chain_s, "batch_per_gpu": B,
+                    "finite": bool(torch.isfinite(out).all())}
+
+    if rank != 0:
+        return
+    burst, sustained, hbm, src = peaks()
+    fwd = fwd_flops_per_image(arch, RES)
+    train_flops = 3 * fwd
+    achieved = img_s / world * train_flops / 1e12  # per GPU
+    roof = {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
+            "traffic": None, "peak_source": f"{src} (sustained bf16; burst {burst})",
+            "scope": "whole train step per GPU (algorithmic 3 x fwd FLOPs/img x img/s); per-kernel numbers in profiles/"}
+    if sampling is not None:
+        s_ach = sampling["image_steps_per_s"] / world * fwd / 1e12
+        sampling["roofline_frac"] = s_ach / sustained
+        sampling["achieved_tflops_per_gpu"] = s_ach
+    line = {"metric": METRIC, "value": img_s, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg_json, "clocks": clk.summary(),
+            "e2e": {"value": img_s_e2e, "unit": "img/s", "h2d_bytes_per_step": host_x.numel() * 4,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e, "last_loss": loss_val},
+            "gpu_launches": int(kernels_per_step * args.steps), "kernels_per_step": int(kernels_per_step),
+            "roofline": roof, "sampling": sampling}
+    if not args.no_cpu_baseline and world == 1:
+        r = cpu_reference_arm(2, 1)
+        line["cpu_baseline"] = {"value": r["train_img_s"], "unit": "img/s", "cores": r["cores"], "kind": "port",
+                                "sample": r["sample"], "samples_per_s": r["samples_s"]}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -75,6 +75,9 @@ typedef struct {
   float* per_sample; /* [B] or NULL */
   float* grad_pred;  /* same layout as pred, or NULL */
   const float* gscale; /* [B] upstream dL/dL_b, needed iff grad_pred */
+  const float* grad_v_unit; /* [B, C, HW] or NULL: if set (c_total == 2C) the variance half of grad_pred becomes
+                               grad_pred[b, C + c, :] = gscale[b] * v_scale * grad_v_unit[b, c, :]  (L_hybrid) */
+  float v_scale;
   int32_t B, C, c_total, hw;
 } pddm_sq_err_params;
 int pddm_sq_err(const pddm_sq_err_params* p, pddm_stream_t stream);

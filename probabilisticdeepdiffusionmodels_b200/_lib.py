@@ -24,6 +24,7 @@ class QSampleParams(C.Structure):
 
 class SqErrParams(C.Structure):
     _fields_ = [("pred", c_vp), ("noise", c_vp), ("per_sample", c_vp), ("grad_pred", c_vp), ("gscale", c_vp),
+                ("grad_v_unit", c_vp), ("v_scale", c_f32),
                 ("B", c_i32), ("C", c_i32), ("c_total", c_i32), ("hw", c_i32)]
 
 
@@ -196,10 +197,14 @@ def dt(t):
     raise TypeError(f"unsupported dtype {t.dtype}")
 
 
-LAUNCHES = [0]  # number of C-ABI compute calls issued from Python (bench.py's gpu_launches claim is derived from it)
+LAUNCHES = [0]  # number of C-ABI compute calls issued from Python
+KERNELS = [0]   # number of kernels those calls launched (bench.py's gpu_launches claim is derived from it)
+# entry points that launch more than one kernel (memsets are not counted)
+_KERNELS_PER_CALL = {"pddm_gn_silu_fwd": 2, "pddm_gn_silu_bwd": 3, "pddm_conv2d_wgrad": 2, "pddm_head_conv_bwd": 2}
 
 
 def call(name, *args):
     lib = load()
     LAUNCHES[0] += 1
+    KERNELS[0] += _KERNELS_PER_CALL.get(name, 1)
     check(getattr(lib, name)(*args), name)

@@ -69,6 +69,11 @@ __global__ void sq_err_kernel(pddm_sq_err_params p) {
     acc += d * d;
     if (gp) gp[i] = -gs * d;
   }
+  if (gp && p.grad_v_unit) {
+    const float vs = p.gscale[b] * p.v_scale;
+    const float* gv = p.grad_v_unit + static_cast<size_t>(b) * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) gp[n + i] = vs * gv[i];
+  }
   acc = block_sum(acc, sh);
   if (threadIdx.x == 0 && p.per_sample) p.per_sample[b] = acc / static_cast<float>(n);
 }

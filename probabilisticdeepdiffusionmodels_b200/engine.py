@@ -1,0 +1,537 @@
+"""``Engine``: the reference's LightningModule surface (src/engine.py:79-657) on top of the sm_100a kernels.
+
+Same constructor arguments, attributes (the 14 fp32 coefficient tables, ``model``, ``ema``, samplers, logs) and
+methods as the reference, so ``scripts/train.py`` / ``sample.py`` / ``eval.py``, the visualisation callback and
+the FID tooling drive it unchanged.  What changed underneath:
+
+* the coefficient tables also live on the device (``DeviceTables``); ``q_sample``, the squared-error loss, the
+  reverse ``p_sample`` step and the variational-bound terms are single fused kernels that gather their
+  per-sample / per-step coefficients on the device (no CPU gather + H2D copy per call);
+* the reverse chain replays ONE CUDA graph per step (UNet forward + p_sample + step bookkeeping) whose step
+  index lives in device memory; the per-step noise still comes from ``torch.randn(generator=...)`` so a seed
+  produces the same stream as the reference on the same device;
+* ``fit_step`` / ``capture_train_step`` run forward + backward + Adam (+EMA) as one CUDA graph.
+
+Extensions (off by default = reference behaviour): ``learn_sigma`` (variance channels + L_hybrid, SURVEY.md
+Appendix C) and ``log_loss_per_t=False`` (skips the reference's per-step device->host sync in ``get_loss``).
+"""
+from contextlib import contextmanager
+from typing import List, Tuple
+
+import numpy as np
+import torch
+
+from . import functional as F
+from . import ops
+from .mathutils import get_generator_if_specified, mean_flat
+from .modules import get_model
+from .schedules import TABLE_NAMES, get_betas, make_tables
+from .timesteps import ImportanceSampler, StepwiseLog, UniformSampler
+from .weight_average import Ema
+
+try:  # the reference subclasses pl.LightningModule; fall back to a minimal stand-in when Lightning is absent
+    import pytorch_lightning as pl
+
+    _Base = pl.LightningModule
+except Exception:  # pragma: no cover - depends on the environment
+
+    class _Base(torch.nn.Module):
+        """Just enough of LightningModule for Engine to be driven by a hand-written loop."""
+
+        @property
+        def device(self):
+            try:
+                return next(self.parameters()).device
+            except StopIteration:
+                return torch.device("cpu")
+
+        def save_hyperparameters(self, *a, **k):
+            pass
+
+        def log(self, name, value, **k):
+            self.__dict__.setdefault("logged", {})[name] = value
+
+        def optimizer_step(self, epoch=None, batch_idx=None, optimizer=None, optimizer_idx=None,
+                           optimizer_closure=None, **k):
+            if optimizer is not None:
+                optimizer.step(closure=optimizer_closure) if optimizer_closure is not None else optimizer.step()
+
+
+LN2 = float(np.log(2.0))
+
+
+class Engine(_Base):
+    def __init__(self, model_config, optimizer_config, diffusion_steps=1000, beta_start=None, beta_end=None,
+                 mode="linear", max_beta=0.999, sigma_mode="beta", resolution=32, clip_while_generating=False,
+                 sampling="uniform", ema=None, scheduler_name=None, scheduler_kwargs=None, learn_sigma=False,
+                 log_loss_per_t=True):
+        super().__init__()
+        self.save_hyperparameters()
+        self.clip_while_generating = clip_while_generating
+        self.learn_sigma = bool(learn_sigma)
+        self.log_loss_per_t = log_loss_per_t
+        cfg = dict(model_config)
+        if self.learn_sigma:
+            cfg["learn_sigma"] = True
+        self.model = get_model(resolution, cfg)
+        if ema is not None:
+            self.ema = Ema(self.model, decay=ema)
+            self.ema.set(self.model)
+        else:
+            self.ema = None
+        self.optimizer_config = optimizer_config
+        self.diffusion_steps = diffusion_steps
+        self.resolution = resolution
+        if sigma_mode not in ("beta", "beta_tilde"):
+            raise ValueError(f"Wrong sigma mode: {sigma_mode}")
+        self.sigma_mode = sigma_mode
+
+        # fp32 CPU tables under the reference's attribute names (src/engine.py:121-150)
+        self._tables = make_tables(get_betas(beta_start, beta_end, diffusion_steps, mode, max_beta=max_beta))
+        for name in TABLE_NAMES:
+            setattr(self, name, self._tables[name])
+        self._dev_tables = {}
+
+        self.loss_per_t = StepwiseLog(diffusion_steps, 10)
+        self.loss_per_t_epoch = StepwiseLog(diffusion_steps)
+        if sampling == "uniform":
+            self.sampler = UniformSampler(diffusion_steps=diffusion_steps)
+        elif sampling == "importance":
+            self.sampler = ImportanceSampler(diffusion_steps=diffusion_steps, loss_per_t=self.loss_per_t, min_counts=10)
+        else:
+            raise ValueError(f'Unknown sampling option: "{sampling}"')
+        self.val_sampler = UniformSampler(diffusion_steps=diffusion_steps)
+        self.scheduler_name = scheduler_name
+        self.scheduler_kwargs = scheduler_kwargs
+        self._chain_graphs = {}
+        self._train_graph = None
+
+    # ------------------------------------------------------------------ plumbing
+    def tabs(self, device=None) -> F.DeviceTables:
+        device = torch.device(device if device is not None else self.device)
+        key = (device.type, device.index)
+        if key not in self._dev_tables:
+            self._dev_tables[key] = F.DeviceTables(self._tables, device)
+        return self._dev_tables[key]
+
+    def _gather(self, name, t, like):
+        """``table[t-1].view(-1,1,1,1)`` on ``like``'s device (the reference's per-call CPU gather, on device)."""
+        tab = self.tabs(like.device).t[name] if like.is_cuda else self._tables[name]
+        idx = torch.as_tensor(t, device=tab.device).long().reshape(-1) - 1
+        return tab[idx].view(-1, 1, 1, 1)
+
+    @contextmanager
+    def ema_on(self):
+        """src/engine.py:171-182"""
+        if self.ema is None:
+            yield
+        else:
+            try:
+                self.original_model = self.model
+                self.model = self.ema.module
+                yield
+            finally:
+                self.model = self.original_model
+                self.original_model = None
+
+    def on_epoch_end(self) -> None:
+        """src/engine.py:184-215 without the matplotlib / wandb plots (out of scope)."""
+        for i in range(4):
+            lo, hi = max(1, int(i * self.diffusion_steps / 4)), int((i + 1) * self.diffusion_steps / 4)
+            try:
+                self.log(f"loss_q{i + 1}", self.loss_per_t_epoch.get_avg_in_range(lo, hi), on_step=False,
+                         on_epoch=True, prog_bar=False)
+            except ValueError:
+                pass
+        self.loss_per_t_epoch.reset()
+
+    def optimizer_step(self, *args, **kwargs):
+        """src/engine.py:217-224"""
+        super().optimizer_step(*args, **kwargs)
+        if self.ema:
+            self.ema.update(self.model)
+
+    def configure_optimizers(self):
+        """src/engine.py:238-248"""
+        optimizer = torch.optim.Adam(self.parameters(), **self.optimizer_config)
+        if self.scheduler_name:
+            scheduler_class = getattr(torch.optim.lr_scheduler, self.scheduler_name)
+            return {"optimizer": optimizer, "lr_scheduler": scheduler_class(optimizer, **self.scheduler_kwargs)}
+        return optimizer
+
+    # ------------------------------------------------------------------ training-side diffusion math
+    def q_mean_std(self, x, t):
+        """src/engine.py:251-257"""
+        return x * self._gather("alphas_hat_sqrt", t, x), self._gather("one_min_alphas_hat_sqrt", t, x)
+
+    def get_q_t(self, x, noise, t):
+        """x_t = sqrt(abar_t) x + sqrt(1-abar_t) noise (src/engine.py:259-261): one fused kernel."""
+        if not x.is_cuda:
+            raise RuntimeError("Engine.get_q_t needs CUDA tensors (sm_100a); there is no CPU fallback")
+        x, noise = x.float().contiguous(), noise.float().contiguous()
+        if isinstance(t, torch.Tensor) and t.numel() == 1:
+            t = int(t.item()) if not torch.cuda.is_current_stream_capturing() else t
+        return F.q_sample(x, noise, t, self.tabs(x.device))
+
+    def per_sample_loss(self, model_out, target_noise, x, x_t, t):
+        """[B] losses: L_simple, or L_simple + (T/1000) L_vlb with learned variance (Appendix C.6)."""
+        if self.learn_sigma:
+            per, _ = ops.HybridLoss.apply(model_out, target_noise.contiguous(), x.contiguous(), x_t.contiguous(), t,
+                                          self.tabs(x.device), self.diffusion_steps / 1000.0)
+            return per
+        return torch.ops.pddm.simple_loss(model_out, target_noise)
+
+    def get_loss(self, predicted_noise, target_noise, x, x_t, t, weights=None, update_loss_log=True):
+        """src/engine.py:263-277"""
+        loss = self.per_sample_loss(predicted_noise, target_noise, x, x_t, t)
+        if update_loss_log and self.log_loss_per_t:
+            losses = loss.detach().cpu().numpy().tolist()  # the reference's per-step host sync
+            ts = t.detach().cpu().numpy().tolist()
+            self.loss_per_t.update_multiple(ts, losses)
+            self.loss_per_t_epoch.update_multiple(ts, losses)
+        if weights is not None:
+            return torch.sum(weights * loss)
+        return torch.mean(loss)
+
+    def training_step(self, batch, batch_idx):  # pylint: disable=unused-argument
+        """src/engine.py:279-307"""
+        x, y = batch
+        t, weights = self.sampler(x.shape[0], self.device)
+        noise = torch.randn_like(x)
+        x_t = self.get_q_t(x, noise, t)
+        predicted_noise = self.model(x_t, t)
+        loss = self.get_loss(predicted_noise, noise, x, x_t, weights=weights, t=t, update_loss_log=True)
+        total_norm = self.compute_grad_norm(self.model.parameters())
+        self.log("loss", loss, on_step=False, on_epoch=True, prog_bar=True)
+        self.log("total_grad_norm_L2", total_norm, on_step=True, on_epoch=False, prog_bar=False)
+        return loss
+
+    def validation_step(self, batch, batch_idx):  # pylint: disable=unused-argument
+        """src/engine.py:309-330"""
+        x, y = batch
+        t, weights = self.val_sampler(x.shape[0], self.device)
+        noise = torch.randn_like(x)
+        x_t = self.get_q_t(x, noise, t)
+        loss = self.get_loss(self.model(x_t, t), noise, x, x_t, weights=weights, t=t, update_loss_log=False)
+        if self.ema is not None:
+            with self.ema_on():
+                predicted_noise = self.model(x_t, t)
+            loss_ema = self.get_loss(predicted_noise, noise, x, x_t, weights=weights, t=t, update_loss_log=False)
+            self.log("val_loss_no_ema", loss, on_step=False, on_epoch=True, prog_bar=False)
+            self.log("val_loss", loss_ema, on_step=False, on_epoch=True, prog_bar=True)
+        else:
+            self.log("val_loss", loss, on_step=False, on_epoch=True, prog_bar=True)
+
+    def compute_grad_norm(self, parameters, norm_type=2):
+        """src/engine.py:332-346 (norm of the previous step's gradients), as two multi-tensor launches."""
+        if isinstance(parameters, torch.Tensor):
+            parameters = [parameters]
+        grads = [p.grad.detach() for p in parameters if p.grad is not None]
+        if not grads:
+            return torch.tensor(0.0)
+        return torch.norm(torch.stack(torch._foreach_norm(grads, float(norm_type))), float(norm_type))
+
+    # ------------------------------------------------------------------ reverse-process pieces (API parity)
+    def get_sigma(self, t):
+        """src/engine.py:354-361 (``t`` is a 0-based index here, like the reference's call ``get_sigma(t_step-1)``)."""
+        if self.sigma_mode == "beta":
+            return torch.sqrt(self.betas[t])
+        elif self.sigma_mode == "beta_tilde":
+            return torch.sqrt(self.posterior_variance[t])
+        raise ValueError(f"Wrong sigma mode: {self.sigma_mode}")
+
+    def xstart_from_epsilon(self, x_t, t, epsilon, clip=False):
+        """src/engine.py:363-368"""
+        x = self._gather("sqrt_recip_alphas_cumprod", t, x_t) * x_t \
+            - self._gather("sqrt_recipm1_alphas_cumprod", t, x_t) * epsilon
+        return x.clamp(-1, 1) if clip else x
+
+    def q_posterior(self, t, x0, x_t):
+        """src/engine.py:477-490"""
+        mean_t = x0 * self._gather("posterior_mean_coef1", t, x_t) + x_t * self._gather("posterior_mean_coef2", t, x_t)
+        return mean_t, self._gather("posterior_variance", t, x_t)
+
+    def model_mean_through_start(self, x_t, t, epsilon, clip=False):
+        """src/engine.py:370-373"""
+        return self.q_posterior(t, self.xstart_from_epsilon(x_t, t, epsilon, clip=clip), x_t)[0]
+
+    def model_mean_from_epsilon(self, x_t, t, epsilon, clip=False):
+        """src/engine.py:375-381"""
+        if clip:
+            return self.model_mean_through_start(x_t, t, epsilon, clip=True)
+        return (x_t - epsilon * self._gather("denoising_coef", t, x_t)) / self._gather("alphas_sqrt", t, x_t)
+
+    def model_mean_std(self, x_t, t, t_step, clip=False):
+        """src/engine.py:348-352"""
+        out = self.model(x_t, t)
+        eps = out[:, : x_t.shape[1]] if self.learn_sigma else out
+        if x_t.is_cuda:
+            mean = F.p_sample_step(x_t.float().contiguous(), out.contiguous(), None, t_step, self.tabs(x_t.device),
+                                   clip, self.sigma_mode)
+        else:
+            mean = self.model_mean_from_epsilon(x_t, t_step, eps, clip=clip)
+        return eps, mean, self.get_sigma(t_step - 1).to(self.device)
+
+    def denoising_step(self, x_t, t_step, mean_only=False, generator=None):
+        """x_{t-1} = mean - sigma * z  (src/engine.py:385-397): UNet forward + one fused kernel."""
+        t = t_step * torch.ones(x_t.shape[0], device=self.device)
+        out = self.model(x_t, t)
+        z = None
+        if not mean_only and t_step > 1:
+            z = torch.randn(x_t.shape, generator=generator, device=self.device, dtype=x_t.dtype)
+        return F.p_sample_step(x_t.float().contiguous(), out.contiguous(), z, t_step, self.tabs(x_t.device),
+                               self.clip_while_generating, "learned" if self.learn_sigma else self.sigma_mode)
+
+    def sample_from_step(self, x_t, t_start, mean_only=False, generator=None, use_graph=True):
+        """src/engine.py:399-403.  With ``use_graph`` the chain replays one captured step (same arithmetic)."""
+        if use_graph and x_t.is_cuda and not torch.is_grad_enabled():
+            return self._chain(x_t, t_start, (), mean_only, generator)[0]
+        for t in range(t_start, 0, -1):
+            x_t = self.denoising_step(x_t, t, mean_only=mean_only, generator=generator)
+        return x_t
+
+    # ------------------------------------------------------------------ graph-replayed reverse chain
+    def _chain_graph(self, shape, dtype, device, mean_only):
+        key = (tuple(shape), str(device), bool(mean_only), id(self.model), self.clip_while_generating,
+               self.sigma_mode, self.learn_sigma)
+        g = self._chain_graphs.get(key)
+        if g is not None:
+            return g
+        st = {"x": torch.zeros(shape, dtype=torch.float32, device=device),
+              "z": None if mean_only else torch.zeros(shape, dtype=torch.float32, device=device),
+              "t_vec": torch.ones(shape[0], dtype=torch.float32, device=device),
+              "t_dev": torch.ones(1, dtype=torch.int32, device=device)}
+        sigma = "learned" if self.learn_sigma else self.sigma_mode
+        tabs = self.tabs(device)
+
+        def step():
+            out = self.model(st["x"], st["t_vec"])
+            F.p_sample_step(st["x"], out, st["z"], -1, tabs, self.clip_while_generating, sigma, out=st["x"],
+                            t_dev=st["t_dev"])
+            F.step_advance(st["t_dev"], st["t_vec"])
+
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(2):  # warm-up: weight packs cached, attributes set, allocator primed
+                st["t_dev"].fill_(1)
+                st["t_vec"].fill_(1.0)
+                step()
+        torch.cuda.current_stream(device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        st["t_dev"].fill_(1)
+        st["t_vec"].fill_(1.0)
+        with torch.cuda.graph(graph):
+            step()
+        st["graph"] = graph
+        self._chain_graphs[key] = st
+        return st
+
+    @torch.no_grad()
+    def _chain(self, x_t, t_start, steps_to_return, mean_only, generator, return_stds=False, fixed_noise=None):
+        was_training = self.model.training
+        self.model.eval()
+        snaps, stds = [], []
+        with ops.frozen_weights():
+            st = self._chain_graph(x_t.shape, x_t.dtype, x_t.device, mean_only)
+            st["x"].copy_(x_t)
+            st["t_dev"].fill_(int(t_start))
+            st["t_vec"].fill_(float(t_start))
+            if return_stds:
+                stds.append(torch.std(x_t).detach().cpu().item())
+            for t in range(t_start, 0, -1):
+                if not mean_only and t > 1:
+                    if fixed_noise is not None:  # parity harness: z for step t is fixed_noise[t_start - t]
+                        st["z"].copy_(fixed_noise[t_start - t])
+                    elif generator is not None:
+                        st["z"].normal_(generator=generator)
+                    else:
+                        st["z"].normal_()
+                st["graph"].replay()
+                if t in steps_to_return:
+                    snaps.append(st["x"].clone())
+                if return_stds:
+                    stds.append(torch.std(st["x"]).detach().cpu().item())
+            out = st["x"].clone()
+        self.model.train(was_training)
+        return out, snaps, stds
+
+    # ------------------------------------------------------------------ NLL evaluation (src/engine.py:407-506)
+    def test_step(self, batch, batch_idx):
+        x, _ = batch
+        with self.ema_on():
+            nll = self.calculate_likelihood(x)
+        for k_out, k_in in (("test_L_0", "L_0"), ("test_L_intermediate", "L_intermediate"), ("test_L_T", "L_T"),
+                            ("test_nll", "nll"), ("test_mse", "MSE")):
+            self.log(k_out, nll[k_in])
+
+    def calculate_likelihood(self, x):
+        """Eq. (5) of DDPM in bits/dim (src/engine.py:417-435)."""
+        L_0 = self._calculate_L_0(x)
+        L_intermediate_list, MSE_list = self._calculate_L_intermediate(x)
+        L_T = self._calculate_L_T(x)
+        L_intermediate = torch.sum(torch.stack(L_intermediate_list), dim=0)
+        return {"MSE": torch.mean(torch.stack(MSE_list)), "MSE_list": MSE_list, "L_0": torch.mean(L_0, dim=0),
+                "L_intermediate": L_intermediate, "L_T": torch.mean(L_T, dim=0),
+                "nll": torch.mean(L_0 + L_intermediate + L_T, dim=0), "L_intermediate_list": L_intermediate_list}
+
+    def _vlb(self, x0, x_t, model_out, t, mode):
+        out, _ = F.vlb_terms(x0.float().contiguous(), None if x_t is None else x_t.contiguous(),
+                             None if model_out is None else model_out.contiguous(), t, self.tabs(x0.device), mode,
+                             self.sigma_mode)
+        return out
+
+    def _calculate_L_T(self, x):
+        """KL(q(x_T|x_0) || N(0, I)) (src/engine.py:437-444)"""
+        return self._vlb(x, None, None, None, 2)
+
+    def _calculate_L_intermediate(self, x0) -> Tuple[List[torch.Tensor], List[torch.Tensor]]:
+        """sum_t KL(q(x_{t-1}|x_t,x_0) || p(x_{t-1}|x_t)), fixed variance (src/engine.py:446-475)"""
+        L_list, MSE_list = [], []
+        ones = torch.ones(x0.shape[0], dtype=torch.int64, device=self.device)
+        for t_step in range(2, self.diffusion_steps + 1):
+            t = ones * t_step
+            noise = torch.randn_like(x0)
+            x_t = self.get_q_t(x0, noise, t)
+            out = self.model(x_t, t)
+            eps = out[:, : x0.shape[1]].contiguous() if self.learn_sigma else out
+            L_list.append(self._vlb(x0, x_t, eps, t, 0))
+            MSE_list.append(torch.pow(eps - noise, 2))
+        return L_list, MSE_list
+
+    def _calculate_L_0(self, x):
+        """-log p(x_0 | x_1) with the discretised Gaussian decoder (src/engine.py:492-506)"""
+        t = torch.ones(x.shape[0], dtype=torch.int64, device=self.device)
+        noise = torch.randn_like(x)
+        x_t = self.get_q_t(x, noise, t)
+        out = self.model(x_t, t)
+        eps = out[:, : x.shape[1]].contiguous() if self.learn_sigma else out
+        return self._vlb(x, x_t, eps, t, 0)
+
+    # ------------------------------------------------------------------ generation endpoints (src/engine.py:508-657)
+    @torch.no_grad()
+    def sample_and_return_steps(self, x_t, t_start=None, steps_to_return=(1,), mean_only=False, generator=None,
+                                seed=None, return_stds=False, fixed_noise=None):
+        """Returns shape [B, STEPS, C, W, H] (CPU tensor, like the reference).  ``fixed_noise`` ([steps, B, C, H, W],
+        extension) injects the per-step z instead of drawing it, so CPU oracle and GPU see identical noise."""
+        if t_start is None:
+            t_start = self.diffusion_steps
+        if generator is None:
+            generator = get_generator_if_specified(seed, device=self.device)
+        assert all(t < t_start for t in steps_to_return)
+        self.eval()
+        _, snaps, stds = self._chain(x_t.to(self.device).float(), t_start, tuple(steps_to_return), mean_only,
+                                     generator, return_stds, fixed_noise)
+        output = torch.zeros((x_t.shape[0], len(steps_to_return)) + tuple(x_t.shape[1:]))
+        for i, s in enumerate(snaps):
+            output[:, i] = s.cpu()
+        return (output, stds) if return_stds else output
+
+    @torch.no_grad()
+    def generate_images(self, n=1, minibatch=4, mean_only=False, seed=None):
+        self.eval()
+        generator = get_generator_if_specified(seed, device=self.device)
+        images = []
+        for _ in range(int(np.ceil(n / minibatch))):
+            x_t = torch.randn((minibatch, self.model.in_channels, self.resolution, self.resolution),
+                              generator=generator, device=self.device)
+            x_t = self.sample_from_step(x_t, self.diffusion_steps, mean_only=mean_only, generator=generator)
+            images.append(x_t.detach().cpu().numpy())
+        return np.concatenate(images, axis=0)
+
+    @torch.no_grad()
+    def generate_images_grid(self, steps_to_return, n=1, minibatch=4, mean_only=False, seed=None):
+        self.eval()
+        generator = get_generator_if_specified(seed, device=self.device)
+        starting_noise, images = [], []
+        for _ in range(int(np.ceil(n / minibatch))):
+            x_t = torch.randn((n, self.model.in_channels, self.resolution, self.resolution), generator=generator,
+                              device=self.device)
+            starting_noise.append(x_t.detach().cpu().numpy())
+            steps = self.sample_and_return_steps(x_t, self.diffusion_steps, steps_to_return=steps_to_return,
+                                                 mean_only=mean_only, generator=generator)
+            images.append(steps.detach().cpu().numpy())
+        return np.concatenate(starting_noise, axis=0), np.concatenate(images, axis=0)
+
+    @torch.no_grad()
+    def get_noised_representation(self, x0, t=None, seed=None, generator=None):
+        if t is None:
+            t = self.diffusion_steps
+        if generator is None:
+            generator = get_generator_if_specified(seed, device=self.device)
+        x0 = x0.to(self.device)
+        noise = torch.randn(x0.shape, generator=generator, device=self.device, dtype=x0.dtype)
+        return self.get_q_t(x0, noise, t)
+
+    @torch.no_grad()
+    def diffuse_and_reconstruct(self, x0, t=None, seed=None):
+        self.eval()
+        if t is None:
+            t = self.diffusion_steps
+        generator = get_generator_if_specified(seed, device=self.device)
+        x_t = self.get_noised_representation(x0, t, generator=generator)
+        return self.sample_from_step(x_t.detach().clone(), t, generator=generator), x_t
+
+    @torch.no_grad()
+    def diffuse_and_reconstruct_grid(self, x0, t_start=None, steps_to_return=(1,), seed=None, mean_only=False,
+                                     return_stds=False):
+        self.eval()
+        if t_start is None:
+            t_start = self.diffusion_steps
+        generator = get_generator_if_specified(seed, device=self.device)
+        x0 = x0.to(self.device)
+        noise = torch.randn(x0.shape, generator=generator, device=self.device, dtype=x0.dtype)
+        x_t = self.get_q_t(x0, noise, t_start)
+        return (self.sample_and_return_steps(x_t.detach().clone(), t_start, steps_to_return, generator=generator,
+                                             mean_only=mean_only, return_stds=return_stds), x_t)
+
+    # ------------------------------------------------------------------ fused training step (forward+backward+Adam)
+    def loss_on(self, x, t, noise, weights=None):
+        """training_step's math with injected (t, noise): q_sample -> UNet -> per-sample loss -> reduction."""
+        x_t = self.get_q_t(x, noise, t)
+        per = self.per_sample_loss(self.model(x_t, t), noise, x, x_t, t)
+        return (torch.sum(weights * per) if weights is not None else torch.mean(per)), per
+
+    def capture_train_step(self, batch_shape, optimizer=None, grad_hook=None):
+        """Capture one optimisation step (t ~ U{1..T}, eps ~ N(0,1) drawn inside the graph, loss, backward,
+        optional ``grad_hook`` (e.g. the data-parallel all-reduce), Adam, EMA) as a CUDA graph.
+        Returns ``step(x) -> loss`` replaying it on a static input buffer."""
+        dev = self.device
+        if optimizer is None:
+            optimizer = torch.optim.Adam(self.model.parameters(), capturable=True, fused=True, **self.optimizer_config)
+        st = {"x": torch.zeros(batch_shape, dtype=torch.float32, device=dev), "opt": optimizer}
+        params = [p for p in self.model.parameters() if p.requires_grad]
+
+        def body():
+            t = torch.randint(1, self.diffusion_steps + 1, (batch_shape[0],), device=dev)
+            noise = torch.randn_like(st["x"])
+            loss, per = self.loss_on(st["x"], t, noise)
+            loss.backward()
+            if grad_hook is not None:
+                grad_hook(params)
+            optimizer.step()
+            if self.ema is not None:
+                self.ema.update(self.model)
+            return loss.detach(), per.detach(), t
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                optimizer.zero_grad(set_to_none=True)
+                body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(graph):
+            st["loss"], st["per"], st["t"] = body()
+        st["graph"] = graph
+        self._train_graph = st
+
+        def step(x):
+            st["x"].copy_(x, non_blocking=True)
+            graph.replay()
+            return st["loss"]
+
+        step.state = st
+        return step

@@ -415,8 +415,9 @@ def q_sample(x0, noise, t, tabs: DeviceTables):
     return out
 
 
-def sq_err(pred, noise, gscale=None, want_grad=False):
-    """per-sample mean (noise - pred[:, :C])^2 ; optionally d/dpred scaled by gscale[b] (other channels zero)."""
+def sq_err(pred, noise, gscale=None, want_grad=False, grad_v_unit=None, v_scale=0.0):
+    """per-sample mean (noise - pred[:, :C])^2 ; optionally d/dpred scaled by gscale[b].  The remaining (variance)
+    channels of the gradient are zero, or gscale[b]*v_scale*grad_v_unit when given (L_hybrid)."""
     L.require_device(pred)
     _chk(pred, f32)
     _chk(noise, f32)
@@ -427,8 +428,11 @@ def sq_err(pred, noise, gscale=None, want_grad=False):
     p = L.SqErrParams()
     p.pred, p.noise, p.per_sample = L.ptr(pred), L.ptr(noise), L.ptr(per)
     if want_grad:
-        grad = torch.zeros_like(pred) if pred.shape[1] != Cc else torch.empty_like(pred)
+        full = pred.shape[1] == Cc or grad_v_unit is not None
+        grad = torch.empty_like(pred) if full else torch.zeros_like(pred)
         p.grad_pred, p.gscale = L.ptr(grad), L.ptr(_chk(gscale, f32))
+        if grad_v_unit is not None:
+            p.grad_v_unit, p.v_scale = L.ptr(_chk(grad_v_unit, f32)), float(v_scale)
     p.B, p.C, p.c_total, p.hw = B, Cc, pred.shape[1], hw
     L.call("pddm_sq_err", C.byref(p), L.stream())
     return per, grad

@@ -487,3 +487,51 @@ def _(x):
 
 torch.library.register_autograd("pddm::to_nhwc", lambda ctx, g: torch.ops.pddm.to_nchw(g))
 torch.library.register_autograd("pddm::to_nchw", lambda ctx, g: torch.ops.pddm.to_nhwc(g))
+
+
+# ================================================================================================ losses
+@torch.library.custom_op("pddm::simple_loss", mutates_args=())
+def simple_loss(pred: Tensor, noise: Tensor) -> Tensor:
+    """per-sample L_simple = mean_flat((noise - pred)^2)  (src/engine.py:266) -> fp32 [B]."""
+    return F.sq_err(pred.contiguous(), noise.contiguous())[0]
+
+
+@simple_loss.register_fake
+def _(pred, noise):
+    return pred.new_empty((pred.shape[0],))
+
+
+@torch.library.custom_op("pddm::simple_loss_bwd", mutates_args=())
+def simple_loss_bwd(pred: Tensor, noise: Tensor, g: Tensor) -> Tensor:
+    return F.sq_err(pred, noise, g.float().contiguous(), want_grad=True)[1]
+
+
+@simple_loss_bwd.register_fake
+def _(pred, noise, g):
+    return pred.new_empty(pred.shape)
+
+
+torch.library.register_autograd(
+    "pddm::simple_loss", lambda ctx, g: (torch.ops.pddm.simple_loss_bwd(*ctx.saved_tensors, g), None),
+    setup_context=lambda ctx, inputs, output: ctx.save_for_backward(inputs[0].contiguous(), inputs[1].contiguous()))
+
+
+class HybridLoss(torch.autograd.Function):
+    """per-sample L_simple + vb_weight * L_vlb with learned variance (SURVEY.md Appendix C): model_out = [eps | v];
+    the variational term sees eps through a stop-gradient, so only v receives its gradient."""
+
+    @staticmethod
+    def forward(ctx, model_out, noise, x0, x_t, t, tabs, vb_weight):
+        model_out = model_out.contiguous()
+        per, _ = F.sq_err(model_out, noise)
+        vb, gv = F.vlb_terms(x0, x_t, model_out, t, tabs, mode=1, want_grad_v=True)
+        ctx.save_for_backward(model_out, noise, gv)
+        ctx.vb_weight = vb_weight
+        return per + vb_weight * vb, vb
+
+    @staticmethod
+    def backward(ctx, g, _gvb):
+        model_out, noise, gv = ctx.saved_tensors
+        _, grad = F.sq_err(model_out, noise, g.float().contiguous(), want_grad=True, grad_v_unit=gv,
+                           v_scale=ctx.vb_weight)
+        return grad, None, None, None, None, None, None
