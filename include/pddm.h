@@ -283,23 +283,25 @@ typedef struct {
 size_t pddm_conv2d_wgrad_workspace(const pddm_wgrad_params* p);
 int pddm_conv2d_wgrad(const pddm_wgrad_params* p, void* workspace, size_t workspace_bytes, pddm_stream_t stream);
 
-/* fp32 parameter [Cout, Cin, kh*kw] -> bf16 GEMM operand.
- *   mode 0 (forward): dst[n, tap, c]            = w[n, c, tap]
- *   mode 1 (dgrad):   dst[c, ntaps-1-tap, n]    = w[n, c, tap]   (flipped taps, transposed channels) */
+/* fp32 parameter [Cout, Cin, kh*kw] -> bf16 GEMM operand, zero-padded to [Cout_pad, ., Cin_pad].
+ *   mode 0 (forward): dst[n, tap, c]            = w[n, c, tap]     dst is [Cout_pad, ntaps, Cin_pad]
+ *   mode 1 (dgrad):   dst[c, ntaps-1-tap, n]    = w[n, c, tap]     dst is [Cin_pad, ntaps, Cout_pad]
+ *                     (flipped taps, transposed channels) */
 int pddm_pack_conv_weight(const float* w, void* dst, int32_t Cout, int32_t Cin, int32_t ntaps, int32_t mode,
-                          pddm_stream_t stream);
+                          int32_t Cout_pad, int32_t Cin_pad, pddm_stream_t stream);
 
-/* Thin convolutions on CUDA cores (too narrow for a UMMA tile): the stem conv Cin<=4 reading the NCHW fp32 model
- * input (src/modules/unet.py:353) and the head conv Cout<=8 writing the NCHW fp32 model output
- * (src/modules/unet.py:440), with their gradients. */
-int pddm_stem_conv_fwd(const float* x_nchw, const float* w, const float* bias, void* y_nhwc_bf16, int32_t B, int32_t Cin,
-                       int32_t H, int32_t W, int32_t Cout, pddm_stream_t stream);
-int pddm_stem_conv_wgrad(const float* x_nchw, const void* dy_nhwc_bf16, float* dw, float* dbias, int32_t B, int32_t Cin,
-                         int32_t H, int32_t W, int32_t Cout, pddm_stream_t stream);
-int pddm_head_conv_fwd(const void* x_nhwc_bf16, const float* w, const float* bias, float* y_nchw, int32_t B, int32_t Cin,
-                       int32_t H, int32_t W, int32_t Cout, pddm_stream_t stream);
-int pddm_head_conv_bwd(const void* x_nhwc_bf16, const float* w, const float* dy_nchw, void* dx_nhwc_bf16, float* dw,
-                       float* dbias, int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t Cout, pddm_stream_t stream);
+/* Helpers that put the two "thin" convolutions on the tensor cores as well: the stem conv (Cin <= 4, reads the
+ * NCHW fp32 model input, src/modules/unet.py:353) becomes a K=32 GEMM over an im2col patch matrix, and the head conv
+ * (Cout <= 8, writes the NCHW fp32 model output, src/modules/unet.py:440) runs with zero-padded output channels.
+ *   im2col3x3: out[b,h,w, ci*9+tap] = x[b,ci,h+dh,w+dw] (bf16 [B,H,W,Kp], zero for k >= Cin*9 and outside the image)
+ *   nchw_to_nhwc_padded: NCHW fp32 [B,C,HW] -> NHWC bf16 [B,HW,Cp], channels >= C zero
+ *   nhwc_slice_to_nchw: first C channels of NHWC fp32 [B,HW,ld] -> NCHW fp32 [B,C,HW] */
+int pddm_im2col3x3(const float* x_nchw, void* out, int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t Kp,
+                   pddm_stream_t stream);
+int pddm_nchw_to_nhwc_padded(const float* src, void* dst, int32_t B, int32_t C, int32_t HW, int32_t Cp,
+                             pddm_stream_t stream);
+int pddm_nhwc_slice_to_nchw(const float* src, float* dst, int32_t B, int32_t C, int32_t HW, int32_t ld,
+                            pddm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * QKVAttention (src/modules/unet.py:237-256): per (sample, head), softmax_fp32((q*s)(k*s)^T) v, s = d^-1/4.

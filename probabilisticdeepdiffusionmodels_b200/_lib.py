@@ -127,11 +127,10 @@ SIGNATURES = {
     "pddm_conv2d_fwd": (c_i32, [P(ConvParams), c_vp]),
     "pddm_conv2d_wgrad_workspace": (c_sz, [P(WgradParams)]),
     "pddm_conv2d_wgrad": (c_i32, [P(WgradParams), c_vp, c_sz, c_vp]),
-    "pddm_pack_conv_weight": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
-    "pddm_stem_conv_fwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
-    "pddm_stem_conv_wgrad": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
-    "pddm_head_conv_fwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
-    "pddm_head_conv_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "pddm_pack_conv_weight": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "pddm_im2col3x3": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "pddm_nchw_to_nhwc_padded": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "pddm_nhwc_slice_to_nchw": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "pddm_attn_fwd": (c_i32, [P(AttnFwdParams), c_vp]),
     "pddm_attn_bwd": (c_i32, [P(AttnBwdParams), c_vp]),
     "pddm_adam_ema_step": (c_i32, [P(AdamParams), c_vp]),
@@ -200,7 +199,7 @@ def dt(t):
 LAUNCHES = [0]  # number of C-ABI compute calls issued from Python
 KERNELS = [0]   # number of kernels those calls launched (bench.py's gpu_launches claim is derived from it)
 # entry points that launch more than one kernel (memsets are not counted)
-_KERNELS_PER_CALL = {"pddm_gn_silu_fwd": 2, "pddm_gn_silu_bwd": 3, "pddm_conv2d_wgrad": 2, "pddm_head_conv_bwd": 2}
+_KERNELS_PER_CALL = {"pddm_gn_silu_fwd": 1, "pddm_gn_silu_bwd": 3, "pddm_conv2d_wgrad": 2}
 
 
 def call(name, *args):

@@ -34,6 +34,8 @@ struct ConvKArgs {
 
 constexpr int kConvThreads = 256;
 constexpr int kMaxStages = 8;
+constexpr int kMaxAddRows = 8;                   // tile rows may span up to this many samples with a staged bias/bcast
+constexpr int kAddBytes = kMaxAddRows * 256 * 4;  // smem for the staged bias + per-sample broadcast vector
 
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -47,6 +49,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tmem_full = bars + 2 * kMaxStages;    // [2]
   uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;  // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  float* smem_add = reinterpret_cast<float*>(smem + a.stages * stage_bytes + 512);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -135,11 +138,16 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
     const int q = warp & 3;
     const int row = q * 32 + lane;
+    const int etid = threadIdx.x - 128;  // 0..127
     int acc = 0;
     uint32_t acc_phase = 0;
     const int rows_per_b = a.BW * a.BH;
+    const int nchunks = a.block_n >> 5;
+    const bool has_add = (a.bias != nullptr) || (a.bcast != nullptr);
+    const bool stage_add = has_add && a.BB <= kMaxAddRows;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_tile = tile % a.m_tiles, n_tile = tile / a.m_tiles;
       const int tw = m_tile % a.tiles_w;
@@ -153,72 +161,112 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const bool valid = (bb < a.BB) && (b < a.B) && (h < a.H) && (w < a.W);
       const size_t opix = (static_cast<size_t>(b) * a.out_H + (h * a.out_sh + a.out_oh)) * a.out_W +
                           (w * a.out_sw + a.out_ow);
+      const int nbase = n_tile * a.block_n;
+      // Stage bias[n] + bcast[b, n] for this tile in shared memory while the MMA main loop is still running,
+      // so the accumulator drain below never waits on a global load.
+      if (stage_add) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers are done
+        const int total = a.BB * a.block_n;
+        for (int i = etid; i < total; i += 128) {
+          const int sb = i / a.block_n, n = nbase + (i - sb * a.block_n);
+          float v = 0.f;
+          if (n < a.Cout) {
+            if (a.bias) v = __ldg(a.bias + n);
+            const int gb = tb * a.BB + sb;
+            if (a.bcast && gb < a.B) v += __ldg(a.bcast + static_cast<size_t>(gb) * a.ld_bcast + n);
+          }
+          smem_add[i] = v;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      const float* addrow = smem_add + (bb < a.BB ? bb : 0) * a.block_n;
+      const bool res_bf16 = a.residual && a.res_dtype == PDDM_BF16;
+      const __nv_bfloat16* res_b = reinterpret_cast<const __nv_bfloat16*>(a.residual) + opix * a.Cout;
+      // prefetch the first residual chunk before blocking on the accumulator
+      uint4 rres[2][4];
+      if (res_bf16 && valid) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          if (nbase + g * 8 < a.Cout) rres[0][g] = __ldg(reinterpret_cast<const uint4*>(res_b + nbase + g * 8));
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * a.block_n;
-      const int nchunks = a.block_n >> 5;
-      for (int c = 0; c < nchunks; ++c) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        tmem_ld_wait();
-        const int n0 = n_tile * a.block_n + c * 32;
-        if (valid && n0 < a.Cout) {
-          float v[32];
+      uint32_t r[2][32];
+      tmem_ld32(taddr, r[0]);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      for (int c = 0; c < 8; ++c) {
+        if (c < nchunks) {
+          tmem_ld_wait();
+          if (c + 1 < nchunks) {
+            tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);  // overlaps with the math/stores of chunk c
+            if (res_bf16 && valid) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int n = n0 + g * 8;
-            if (n < a.Cout) {
-              if (a.bias) {
-                const float4 b0v = __ldg(reinterpret_cast<const float4*>(a.bias + n));
-                const float4 b1v = __ldg(reinterpret_cast<const float4*>(a.bias + n + 4));
-                v[g * 8 + 0] += b0v.x; v[g * 8 + 1] += b0v.y; v[g * 8 + 2] += b0v.z; v[g * 8 + 3] += b0v.w;
-                v[g * 8 + 4] += b1v.x; v[g * 8 + 5] += b1v.y; v[g * 8 + 6] += b1v.z; v[g * 8 + 7] += b1v.w;
+              for (int g = 0; g < 4; ++g)
+                if (nbase + (c + 1) * 32 + g * 8 < a.Cout)
+                  rres[(c + 1) & 1][g] = __ldg(reinterpret_cast<const uint4*>(res_b + nbase + (c + 1) * 32 + g * 8));
+            }
+          }
+          const int n0 = nbase + c * 32;
+          if (valid && n0 < a.Cout) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[c & 1][j]);
+            if (stage_add) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 av = *reinterpret_cast<const float4*>(addrow + c * 32 + j);
+                v[j] += av.x; v[j + 1] += av.y; v[j + 2] += av.z; v[j + 3] += av.w;
               }
-              if (a.bcast) {
-                const float* bp = a.bcast + static_cast<size_t>(b) * a.ld_bcast + n;
-                const float4 b0v = __ldg(reinterpret_cast<const float4*>(bp));
-                const float4 b1v = __ldg(reinterpret_cast<const float4*>(bp + 4));
-                v[g * 8 + 0] += b0v.x; v[g * 8 + 1] += b0v.y; v[g * 8 + 2] += b0v.z; v[g * 8 + 3] += b0v.w;
-                v[g * 8 + 4] += b1v.x; v[g * 8 + 5] += b1v.y; v[g * 8 + 6] += b1v.z; v[g * 8 + 7] += b1v.w;
-              }
-              if (a.residual) {
-                if (a.res_dtype == PDDM_BF16) {
-                  const uint4 rv = __ldg(reinterpret_cast<const uint4*>(
-                      reinterpret_cast<const __nv_bfloat16*>(a.residual) + opix * a.Cout + n));
-                  const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+            }
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
-                    v[g * 8 + 2 * j] += __low2float(h2);
-                    v[g * 8 + 2 * j + 1] += __high2float(h2);
+            for (int g = 0; g < 4; ++g) {
+              const int n = n0 + g * 8;
+              if (n < a.Cout) {
+                if (has_add && !stage_add) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    if (a.bias) v[g * 8 + j] += __ldg(a.bias + n + j);
+                    if (a.bcast) v[g * 8 + j] += __ldg(a.bcast + static_cast<size_t>(b) * a.ld_bcast + n + j);
                   }
-                } else {
-                  const float* rp = reinterpret_cast<const float*>(a.residual) + opix * a.Cout + n;
-                  const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));
-                  const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + 4));
-                  v[g * 8 + 0] += r0.x; v[g * 8 + 1] += r0.y; v[g * 8 + 2] += r0.z; v[g * 8 + 3] += r0.w;
-                  v[g * 8 + 4] += r1.x; v[g * 8 + 5] += r1.y; v[g * 8 + 6] += r1.z; v[g * 8 + 7] += r1.w;
                 }
-              }
-              if (a.y_dtype == PDDM_BF16) {
-                uint4 o;
-                o.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
-                o.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
-                o.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
-                o.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
-                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.y) + opix * a.Cout + n) = o;
-              } else {
-                float* yp = reinterpret_cast<float*>(a.y) + opix * a.Cout + n;
-                *reinterpret_cast<float4*>(yp) = make_float4(v[g * 8 + 0], v[g * 8 + 1], v[g * 8 + 2], v[g * 8 + 3]);
-                *reinterpret_cast<float4*>(yp + 4) =
-                    make_float4(v[g * 8 + 4], v[g * 8 + 5], v[g * 8 + 6], v[g * 8 + 7]);
+                if (a.residual) {
+                  if (res_bf16) {
+                    const uint4 rv = rres[c & 1][g];
+                    const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
+                      v[g * 8 + 2 * j] += __low2float(h2);
+                      v[g * 8 + 2 * j + 1] += __high2float(h2);
+                    }
+                  } else {
+                    const float* rp = reinterpret_cast<const float*>(a.residual) + opix * a.Cout + n;
+                    const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));
+                    const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + 4));
+                    v[g * 8 + 0] += r0.x; v[g * 8 + 1] += r0.y; v[g * 8 + 2] += r0.z; v[g * 8 + 3] += r0.w;
+                    v[g * 8 + 4] += r1.x; v[g * 8 + 5] += r1.y; v[g * 8 + 6] += r1.z; v[g * 8 + 7] += r1.w;
+                  }
+                }
+                if (a.y_dtype == PDDM_BF16) {
+                  uint4 o;
+                  o.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
+                  o.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+                  o.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
+                  o.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+                  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.y) + opix * a.Cout + n) = o;
+                } else {
+                  float* yp = reinterpret_cast<float*>(a.y) + opix * a.Cout + n;
+                  *reinterpret_cast<float4*>(yp) = make_float4(v[g * 8 + 0], v[g * 8 + 1], v[g * 8 + 2], v[g * 8 + 3]);
+                  *reinterpret_cast<float4*>(yp + 4) =
+                      make_float4(v[g * 8 + 4], v[g * 8 + 5], v[g * 8 + 6], v[g * 8 + 7]);
+                }
               }
             }
           }
         }
       }
+      // all of this warp's TMEM reads have completed (last tmem_ld_wait): hand the accumulator back
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -285,6 +333,10 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
   const int tiles_b = (p->B + a.BB - 1) / a.BB;
   a.m_tiles = a.tiles_w * a.tiles_h * tiles_b;
   a.block_n = pick_block_n(p->Cout);
+  // small spatial extents: trade B-operand reuse for enough tiles to occupy every SM
+  while (a.block_n % 64 == 0 &&
+         a.m_tiles * ((p->Cout + a.block_n / 2 - 1) / (a.block_n / 2)) <= device_info().sm_count)
+    a.block_n /= 2;
   a.n_tiles = (p->Cout + a.block_n - 1) / a.block_n;
   a.bk = (p->Cin % 64 == 0) ? 64 : 32;
   a.kblocks_per_tap = p->Cin / a.bk;
@@ -309,12 +361,12 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
   while (cols < static_cast<uint32_t>(2 * a.block_n)) cols <<= 1;
   a.tmem_cols = cols;
   const int stage_bytes = a.a_slot_bytes + a.b_bytes;
-  const int budget = device_info().max_smem_optin - 1024 - 512;
+  const int budget = device_info().max_smem_optin - 1024 - 512 - kAddBytes;
   int stages = budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return PDDM_ERR_UNSUPPORTED;
   a.stages = stages;
-  const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 + 512;
+  const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 + 512 + kAddBytes;
 
   CUtensorMap tmA, tmB;
   {

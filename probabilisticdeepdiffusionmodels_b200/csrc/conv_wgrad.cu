@@ -197,22 +197,31 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   }
 }
 
-// dw[layout] (+)= sum_s partial[s][n][tap][c]
+// dw[layout] (+)= sum_s partial[s][n][tap][c]   (fixed summation order: deterministic; 4 channels per thread)
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int Cout,
                                     int ntaps, int Cin, int layout, int accumulate) {
-  const size_t total = static_cast<size_t>(Cout) * ntaps * Cin;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    float s = 0.f;
-    for (int k = 0; k < splits; ++k) s += partial[k * total + i];
-    size_t o = i;
-    if (layout == 1) {
+  const size_t total4 = static_cast<size_t>(Cout) * ntaps * Cin / 4;
+  for (size_t i4 = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i4 < total4;
+       i4 += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < splits; ++k) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(partial) + k * total4 + i4);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    const size_t i = i4 * 4;
+    if (layout == 0) {
+      float4* o = reinterpret_cast<float4*>(dw) + i4;
+      if (accumulate) { const float4 d = *o; s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w; }
+      *o = s;
+    } else {
       const int c = static_cast<int>(i % Cin);
       const int tap = static_cast<int>((i / Cin) % ntaps);
       const int n = static_cast<int>(i / (static_cast<size_t>(Cin) * ntaps));
-      o = (static_cast<size_t>(n) * Cin + c) * ntaps + tap;
+      float* o = dw + (static_cast<size_t>(n) * Cin + c) * ntaps + tap;
+      const float v[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j * ntaps] = accumulate ? o[j * ntaps] + v[j] : v[j];
     }
-    dw[o] = accumulate ? dw[o] + s : s;
   }
 }
 
@@ -254,7 +263,7 @@ static int plan_wgrad(const pddm_wgrad_params* p, WgradPlan* plan) {
   }
   const int base_items = a.ntaps * a.m_tiles * a.n_tiles;
   const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
-  int splits = (2 * sms + base_items - 1) / base_items;  // aim at ~2 waves of work items
+  int splits = sms / base_items;  // one wave of work items: every extra split costs a full fp32 partial tile
   const int max_splits = (a.k_blocks + 7) / 8;           // but keep >= 8 K-blocks per split
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
@@ -331,8 +340,9 @@ extern "C" int pddm_conv2d_wgrad(const pddm_wgrad_params* p, void* workspace, si
   conv_wgrad_kernel<<<plan.grid, kWgThreads, plan.smem_bytes, stream>>>(tmDY, tmX, plan.a);
   if (cudaPeekAtLastError() != cudaSuccess) return PDDM_ERR_CUDA;
   const size_t total = static_cast<size_t>(p->Cout) * p->ntaps * p->Cin;
-  int blocks = static_cast<int>((total + 255) / 256);
-  if (blocks > 4096) blocks = 4096;
+  int blocks = static_cast<int>((total / 4 + 255) / 256);
+  if (blocks > 2368) blocks = 2368;
+  if (blocks < 1) blocks = 1;
   wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(plan.a.partial, p->dw, plan.a.splits, p->Cout, p->ntaps, p->Cin,
                                                   p->dw_layout, p->accumulate);
   return launch_status();

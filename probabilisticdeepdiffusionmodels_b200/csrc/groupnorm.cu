@@ -1,78 +1,95 @@
 // GroupNorm(32) [+ per-sample scale/shift] [+ SiLU], forward and backward, on NHWC activations.
 //
-// HBM-bound.  Thread mapping: a thread owns one 8-channel vector (16 B of bf16 / 32 B of fp32) and walks down
-// the pixels of its sample slab, so a warp always touches one fully contiguous span of memory.  Statistics are
-// accumulated per channel in registers, folded to groups through shared memory, and exchanged between the
-// CTAs of one sample through a small [B, S, ...] partials array that the second pass re-reads (the tensor
-// itself is re-read from L2: at B=128 every activation of the CIFAR config fits in the 126 MB L2).
+// HBM-bound elementwise + reduction work.  One sample is processed by a thread-block CLUSTER of S CTAs
+// (S in {1,2,4,8}); each CTA owns a slab of pixels.  A thread owns 4 consecutive channels (8 B of bf16 / 16 B of
+// fp32) and walks down its slab, so every warp touches one contiguous span and the register footprint stays small
+// enough for 3-4 resident CTAs per SM.  Partial sums are folded lanes -> channels -> (groups) in shared memory and
+// exchanged between the CTAs of the cluster through distributed shared memory in rank order: deterministic, no
+// global staging, and the whole op is ONE kernel (statistics pass from HBM, exchange, normalisation pass re-reading
+// the slab from L2).  The backward stores dzn = dL/d(gamma*xhat+beta) in the dx buffer during its first pass so the
+// second pass needs neither dy nor the activation derivative again.
 #include <cuda_bf16.h>
+#include <string.h>
 
 #include "host_common.h"
 
 namespace pddm {
 
 typedef __nv_bfloat16 bf16;
-constexpr int kMaxSplit = 16;
+constexpr int CH = 4;  // channels per thread
 
-__device__ __forceinline__ void load8(const void* base, int dtype, size_t elem_off, float* f) {
+__device__ __forceinline__ void load4(const void* base, int dtype, size_t elem_off, float* f) {
   if (dtype == PDDM_BF16) {
-    const uint4 v = *reinterpret_cast<const uint4*>(static_cast<const bf16*>(base) + elem_off);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      f[2 * i] = __low2float(h[i]);
-      f[2 * i + 1] = __high2float(h[i]);
-    }
+    const uint2 v = *reinterpret_cast<const uint2*>(static_cast<const bf16*>(base) + elem_off);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
+    f[0] = __low2float(a); f[1] = __high2float(a); f[2] = __low2float(b); f[3] = __high2float(b);
   } else {
     const float4 a = *reinterpret_cast<const float4*>(static_cast<const float*>(base) + elem_off);
-    const float4 b = *reinterpret_cast<const float4*>(static_cast<const float*>(base) + elem_off + 4);
-    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
   }
 }
-__device__ __forceinline__ void store8(void* base, int dtype, size_t elem_off, const float* f) {
+__device__ __forceinline__ void store4(void* base, int dtype, size_t elem_off, const float* f) {
   if (dtype == PDDM_BF16) {
-    uint4 v;
-    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-    *reinterpret_cast<uint4*>(static_cast<bf16*>(base) + elem_off) = v;
+    uint2 v;
+    *reinterpret_cast<__nv_bfloat162*>(&v.x) = __floats2bfloat162_rn(f[0], f[1]);
+    *reinterpret_cast<__nv_bfloat162*>(&v.y) = __floats2bfloat162_rn(f[2], f[3]);
+    *reinterpret_cast<uint2*>(static_cast<bf16*>(base) + elem_off) = v;
   } else {
-    float* p = static_cast<float*>(base) + elem_off;
-    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
-    *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+    *reinterpret_cast<float4*>(static_cast<float*>(base) + elem_off) = make_float4(f[0], f[1], f[2], f[3]);
   }
 }
+__device__ __forceinline__ float fast_sigmoid(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
 
 struct GnGeom {
-  int B, HW, C, G, cpg, C8, nlanes, S, rows_per_cta;
+  int B, HW, C, G, cpg, CV, nlanes, S, rows_per_cta;
 };
 
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_peer_smem(const float* local_ptr, int rank) {
+  uint32_t laddr = static_cast<uint32_t>(__cvta_generic_to_shared(local_ptr)), raddr;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(raddr) : "memory");
+  return v;
+}
+
 // ------------------------------------------------------------------------------------------------ forward
-// pass 1: per (sample, split) partial group sums -> part[b][s][g][2]
-__global__ void gn_stats_kernel(const void* __restrict__ x, int x_dtype, float* __restrict__ part, GnGeom g) {
-  extern __shared__ float sh[];  // [2][nlanes][C]
-  const int b = blockIdx.y, s = blockIdx.x;
-  const int cv = threadIdx.x % g.C8, lr = threadIdx.x / g.C8;
-  float sum[8], sq[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
+template <bool SILU, bool SS>
+__global__ void __launch_bounds__(256, 4) gn_fwd_cluster_kernel(pddm_gn_fwd_params p, GnGeom g) {
+  extern __shared__ float sh[];  // scratch[2][nlanes][C] | part[G][2] | stat[G][2]
+  const int b = blockIdx.y, s = blockIdx.x;  // s = rank in the cluster
+  const int cv = threadIdx.x % g.CV, lr = threadIdx.x / g.CV;
+  float* sh_sum = sh;
+  float* sh_sq = sh + g.nlanes * g.C;
+  float* part = sh + 2 * g.nlanes * g.C;
+  float* stat = part + 2 * g.G;
   const int r0 = s * g.rows_per_cta, r1 = min(r0 + g.rows_per_cta, g.HW);
-  for (int r = r0 + lr; r < r1; r += g.nlanes) {
-    float f[8];
-    load8(x, x_dtype, (static_cast<size_t>(b) * g.HW + r) * g.C + cv * 8, f);
+  const size_t base = static_cast<size_t>(b) * g.HW * g.C + cv * CH;
+  float sum[CH], sq[CH];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      sum[j] += f[j];
-      sq[j] += f[j] * f[j];
-    }
+  for (int j = 0; j < CH; ++j) sum[j] = sq[j] = 0.f;
+  for (int r = r0 + lr; r < r1; r += 4 * g.nlanes) {  // 4 independent vector loads in flight per thread
+    float f[4][CH];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (r + u * g.nlanes < r1) load4(p.x, p.x_dtype, base + static_cast<size_t>(r + u * g.nlanes) * g.C, f[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (r + u * g.nlanes < r1) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          sum[j] += f[u][j];
+          sq[j] += f[u][j] * f[u][j];
+        }
+      }
   }
-  // fixed-order (deterministic) fold: lanes -> channels -> groups
-  float* sh_sum = sh;                       // [nlanes][C]
-  float* sh_sq = sh + g.nlanes * g.C;       // [nlanes][C]
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    sh_sum[lr * g.C + cv * 8 + j] = sum[j];
-    sh_sq[lr * g.C + cv * 8 + j] = sq[j];
+  for (int j = 0; j < CH; ++j) {
+    sh_sum[lr * g.C + cv * CH + j] = sum[j];
+    sh_sq[lr * g.C + cv * CH + j] = sq[j];
   }
   __syncthreads();
   for (int gi = threadIdx.x; gi < g.G; gi += blockDim.x) {
@@ -82,59 +99,64 @@ __global__ void gn_stats_kernel(const void* __restrict__ x, int x_dtype, float* 
         a += sh_sum[l * g.C + c];
         q += sh_sq[l * g.C + c];
       }
-    float* o = part + ((static_cast<size_t>(b) * g.S + s) * g.G + gi) * 2;
-    o[0] = a;
-    o[1] = q;
+    part[gi * 2] = a;
+    part[gi * 2 + 1] = q;
   }
-}
-
-// pass 2: normalise + affine (+ scale/shift) (+ SiLU)
-__global__ void gn_apply_kernel(pddm_gn_fwd_params p, const float* __restrict__ part, GnGeom g) {
-  extern __shared__ float sh[];  // mean[G], rstd[G]
-  const int b = blockIdx.y, s = blockIdx.x;
+  if (g.S > 1) cluster_sync_all(); else __syncthreads();
   for (int gi = threadIdx.x; gi < g.G; gi += blockDim.x) {
     float a = 0.f, q = 0.f;
-    for (int k = 0; k < g.S; ++k) {
-      const float* o = part + ((static_cast<size_t>(b) * g.S + k) * g.G + gi) * 2;
-      a += o[0];
-      q += o[1];
+    if (g.S > 1) {
+      for (int k = 0; k < g.S; ++k) {
+        a += ld_peer_smem(part + gi * 2, k);
+        q += ld_peer_smem(part + gi * 2 + 1, k);
+      }
+    } else {
+      a = part[gi * 2];
+      q = part[gi * 2 + 1];
     }
     const float n = static_cast<float>(g.cpg) * g.HW;
     const float mean = a / n;
     const float var = fmaxf(q / n - mean * mean, 0.f);
     const float rstd = rsqrtf(var + p.eps);
-    sh[gi] = mean;
-    sh[g.G + gi] = rstd;
+    stat[gi] = mean;
+    stat[g.G + gi] = rstd;
     if (s == 0) {
       p.mean[b * g.G + gi] = mean;
       p.rstd[b * g.G + gi] = rstd;
     }
   }
-  __syncthreads();
-  const int cv = threadIdx.x % g.C8, lr = threadIdx.x / g.C8;
-  float ga[8], be[8], mu[8], rs[8], sc[8], sf[8];
+  if (g.S > 1) cluster_sync_all(); else __syncthreads();  // peers are done reading this CTA's partials
+  // y = ((x - mean) * rstd * gamma + beta) [* (1 + scale) + shift]  ==  x * a + c  with per-channel a, c
+  float ca[CH], cc[CH];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = cv * 8 + j;
-    ga[j] = p.gamma[c];
-    be[j] = p.beta[c];
-    mu[j] = sh[c / g.cpg];
-    rs[j] = sh[g.G + c / g.cpg];
-    sc[j] = p.scale ? 1.f + p.scale[static_cast<size_t>(b) * p.ld_ss + c] : 1.f;
-    sf[j] = p.shift ? p.shift[static_cast<size_t>(b) * p.ld_ss + c] : 0.f;
-  }
-  const int r0 = s * g.rows_per_cta, r1 = min(r0 + g.rows_per_cta, g.HW);
-  for (int r = r0 + lr; r < r1; r += g.nlanes) {
-    const size_t off = (static_cast<size_t>(b) * g.HW + r) * g.C + cv * 8;
-    float f[8];
-    load8(p.x, p.x_dtype, off, f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float z = (f[j] - mu[j]) * rs[j] * ga[j] + be[j];
-      z = z * sc[j] + sf[j];
-      f[j] = p.silu ? z / (1.f + __expf(-z)) : z;
+  for (int j = 0; j < CH; ++j) {
+    const int c = cv * CH + j;
+    const float mu = stat[c / g.cpg], rs = stat[g.G + c / g.cpg];
+    float a = rs * p.gamma[c];
+    float o = p.beta[c] - mu * a;
+    if (SS) {
+      const float sc = 1.f + p.scale[static_cast<size_t>(b) * p.ld_ss + c];
+      a *= sc;
+      o = o * sc + p.shift[static_cast<size_t>(b) * p.ld_ss + c];
     }
-    store8(p.y, PDDM_BF16, off, f);
+    ca[j] = a;
+    cc[j] = o;
+  }
+  for (int r = r0 + lr; r < r1; r += 4 * g.nlanes) {
+    float f[4][CH];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (r + u * g.nlanes < r1) load4(p.x, p.x_dtype, base + static_cast<size_t>(r + u * g.nlanes) * g.C, f[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (r + u * g.nlanes < r1) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          const float z = f[u][j] * ca[j] + cc[j];
+          f[u][j] = SILU ? z * fast_sigmoid(z) : z;
+        }
+        store4(p.y, PDDM_BF16, base + static_cast<size_t>(r + u * g.nlanes) * g.C, f[u]);
+      }
   }
 }
 
@@ -145,93 +167,100 @@ __global__ void gn_apply_kernel(pddm_gn_fwd_params p, const float* __restrict__ 
 //   S1_g = sum_{c in g} gamma_c A_c;  S2_g = sum_{c in g} gamma_c Bq_c;  n = cpg*HW
 //   dx = rstd*(gamma_c*dzn - (S1_g + xh*S2_g)/n);  dgamma_c = sum_b Bq_c;  dbeta_c = sum_b A_c
 //   sum_hw dx = rstd*(gamma_c*A_c - (HW*S1_g + S2_g*Xh_c)/n)
-// pass 1 writes part[b][s][5][C] = {A, Bq, Xh, dshift, dscale}
-__global__ void gn_bwd_stats_kernel(pddm_gn_bwd_params p, float* __restrict__ part, GnGeom g) {
-  extern __shared__ float sh[];  // [5][nlanes][C]
+// Rank 0 of each cluster writes the per-sample channel totals tot[b][5][C] = {A, Bq, Xh, dshift, dscale}.
+// Pass 1 parks dzn in the dx buffer (rounded to dx's dtype); pass 2 turns it into dx in place.
+template <bool SILU, bool SS>
+__global__ void __launch_bounds__(256, 3) gn_bwd_cluster_kernel(pddm_gn_bwd_params p, float* __restrict__ tot, GnGeom g) {
+  extern __shared__ float sh[];  // scratch[NQ][nlanes][C] | part[5][C] | sA[C] sB[C] | S1[G] S2[G]
+  constexpr int NQ = SS ? 5 : 3;
   const int b = blockIdx.y, s = blockIdx.x;
-  const int cv = threadIdx.x % g.C8, lr = threadIdx.x / g.C8;
-  float ga[8], be[8], mu[8], rs[8], sc[8], sf[8];
-  float A[8], Bq[8], Xh[8], Ds[8], Dc[8];
+  const int cv = threadIdx.x % g.CV, lr = threadIdx.x / g.CV;
+  const int LC = g.nlanes * g.C;
+  float* part = sh + NQ * LC;
+  float* sA = part + 5 * g.C;
+  float* sB = sA + g.C;
+  float* sS1 = sB + g.C;
+  float* sS2 = sS1 + g.G;
+  const size_t base = static_cast<size_t>(b) * g.HW * g.C + cv * CH;
+  // xh = x*xa + xc ;  z = xh*za + zc (za = gamma*(1+scale), zc = beta*(1+scale)+shift)
+  float xa[CH], xc[CH], za[CH], zc[CH], sc1[CH], gam[CH], bet[CH];
+  float acc[NQ][CH];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = cv * 8 + j;
-    ga[j] = p.gamma[c];
-    be[j] = p.beta[c];
-    mu[j] = p.mean[b * g.G + c / g.cpg];
-    rs[j] = p.rstd[b * g.G + c / g.cpg];
-    sc[j] = p.scale ? 1.f + p.scale[static_cast<size_t>(b) * p.ld_ss + c] : 1.f;
-    sf[j] = p.shift ? p.shift[static_cast<size_t>(b) * p.ld_ss + c] : 0.f;
-    A[j] = Bq[j] = Xh[j] = Ds[j] = Dc[j] = 0.f;
+  for (int j = 0; j < CH; ++j) {
+    const int c = cv * CH + j;
+    const float mu = p.mean[b * g.G + c / g.cpg], rs = p.rstd[b * g.G + c / g.cpg];
+    xa[j] = rs;
+    xc[j] = -mu * rs;
+    gam[j] = p.gamma[c];
+    bet[j] = p.beta[c];
+    sc1[j] = SS ? 1.f + p.scale[static_cast<size_t>(b) * p.ld_ss + c] : 1.f;
+    za[j] = gam[j] * sc1[j];
+    zc[j] = bet[j] * sc1[j] + (SS ? p.shift[static_cast<size_t>(b) * p.ld_ss + c] : 0.f);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) acc[q][j] = 0.f;
   }
   const int r0 = s * g.rows_per_cta, r1 = min(r0 + g.rows_per_cta, g.HW);
-  for (int r = r0 + lr; r < r1; r += g.nlanes) {
-    const size_t off = (static_cast<size_t>(b) * g.HW + r) * g.C + cv * 8;
-    float f[8], d[8];
-    load8(p.x, p.x_dtype, off, f);
-    load8(p.dy, PDDM_BF16, off, d);
+  for (int r = r0 + lr; r < r1; r += 2 * g.nlanes) {
+    float f[2][CH], d[2][CH];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xh = (f[j] - mu[j]) * rs[j];
-      const float zn = xh * ga[j] + be[j];
-      const float z = zn * sc[j] + sf[j];
-      float dz = d[j];
-      if (p.silu) {
-        const float sg = 1.f / (1.f + __expf(-z));
-        dz *= sg * (1.f + z * (1.f - sg));
+    for (int u = 0; u < 2; ++u)
+      if (r + u * g.nlanes < r1) {
+        const size_t off = base + static_cast<size_t>(r + u * g.nlanes) * g.C;
+        load4(p.x, p.x_dtype, off, f[u]);
+        load4(p.dy, PDDM_BF16, off, d[u]);
       }
-      const float dzn = dz * sc[j];
-      A[j] += dzn;
-      Bq[j] += dzn * xh;
-      Xh[j] += xh;
-      Ds[j] += dz;
-      Dc[j] += dz * zn;
-    }
-  }
-  // fixed-order (deterministic) fold over the pixel lanes: sh[q][lane][C]
-  const int LC = g.nlanes * g.C;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = lr * g.C + cv * 8 + j;
-    sh[c] = A[j];
-    sh[LC + c] = Bq[j];
-    sh[2 * LC + c] = Xh[j];
-    sh[3 * LC + c] = Ds[j];
-    sh[4 * LC + c] = Dc[j];
+    for (int u = 0; u < 2; ++u)
+      if (r + u * g.nlanes < r1) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          const float xh = f[u][j] * xa[j] + xc[j];
+          float dz = d[u][j];
+          if (SILU) {
+            const float z = xh * za[j] + zc[j];
+            const float sg = fast_sigmoid(z);
+            dz *= sg * (1.f + z * (1.f - sg));
+          }
+          const float dzn = dz * sc1[j];
+          acc[0][j] += dzn;
+          acc[1][j] += dzn * xh;
+          acc[2][j] += xh;
+          if (SS) {
+            acc[3][j] += dz;
+            acc[4][j] += dz * (xh * gam[j] + bet[j]);
+          }
+          d[u][j] = dzn;
+        }
+        store4(p.dx, p.dx_dtype, base + static_cast<size_t>(r + u * g.nlanes) * g.C, d[u]);
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < CH; ++j) {
+    const int c = lr * g.C + cv * CH + j;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) sh[q * LC + c] = acc[q][j];
   }
   __syncthreads();
-  float* o = part + (static_cast<size_t>(b) * g.S + s) * 5 * g.C;
   for (int i = threadIdx.x; i < 5 * g.C; i += blockDim.x) {
     const int q = i / g.C, c = i - q * g.C;
     float v = 0.f;
-    for (int l = 0; l < g.nlanes; ++l) v += sh[q * LC + l * g.C + c];
-    o[i] = v;
+    if (q < NQ)
+      for (int l = 0; l < g.nlanes; ++l) v += sh[q * LC + l * g.C + c];
+    part[i] = v;
   }
-}
-
-// pass 2: dx; CTA s == 0 of each sample also emits the per-sample channel totals tot[b][5][C]
-__global__ void gn_bwd_apply_kernel(pddm_gn_bwd_params p, const float* __restrict__ part, float* __restrict__ tot,
-                                    GnGeom g) {
-  extern __shared__ float sh[];  // A[C], Bq[C], S1[G], S2[G]
-  const int b = blockIdx.y, s = blockIdx.x;
-  float* sA = sh;
-  float* sB = sh + g.C;
-  float* sS1 = sh + 2 * g.C;
-  float* sS2 = sh + 2 * g.C + g.G;
-  for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
-    float v[5] = {0, 0, 0, 0, 0};
-    for (int k = 0; k < g.S; ++k) {
-      const float* o = part + (static_cast<size_t>(b) * g.S + k) * 5 * g.C;
-#pragma unroll
-      for (int q = 0; q < 5; ++q) v[q] += o[q * g.C + c];
+  if (g.S > 1) cluster_sync_all(); else __syncthreads();
+  for (int i = threadIdx.x; i < 5 * g.C; i += blockDim.x) {
+    float v = 0.f;
+    if (g.S > 1) {
+      for (int k = 0; k < g.S; ++k) v += ld_peer_smem(part + i, k);
+    } else {
+      v = part[i];
     }
-    sA[c] = v[0];
-    sB[c] = v[1];
-    if (s == 0) {
-#pragma unroll
-      for (int q = 0; q < 5; ++q) tot[(static_cast<size_t>(b) * 5 + q) * g.C + c] = v[q];
-    }
+    if (i < g.C) sA[i] = v;
+    else if (i < 2 * g.C) sB[i - g.C] = v;
+    if (s == 0) tot[static_cast<size_t>(b) * 5 * g.C + i] = v;
   }
-  __syncthreads();
+  if (g.S > 1) cluster_sync_all(); else __syncthreads();
   for (int gi = threadIdx.x; gi < g.G; gi += blockDim.x) {
     float s1 = 0.f, s2 = 0.f;
     for (int c = gi * g.cpg; c < (gi + 1) * g.cpg; ++c) {
@@ -242,119 +271,155 @@ __global__ void gn_bwd_apply_kernel(pddm_gn_bwd_params p, const float* __restric
     sS2[gi] = s2;
   }
   __syncthreads();
-  const int cv = threadIdx.x % g.C8, lr = threadIdx.x / g.C8;
+  // dx = rs*gamma*dzn - rs*(s1 + xh*s2)/n  =  dzn*da + x*db + dc
   const float inv_n = 1.f / (static_cast<float>(g.cpg) * g.HW);
-  float ga[8], be[8], mu[8], rs[8], sc[8], sf[8], s1[8], s2[8];
+  float da[CH], db[CH], dc[CH];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = cv * 8 + j, gi = c / g.cpg;
-    ga[j] = p.gamma[c];
-    be[j] = p.beta[c];
-    mu[j] = p.mean[b * g.G + gi];
-    rs[j] = p.rstd[b * g.G + gi];
-    sc[j] = p.scale ? 1.f + p.scale[static_cast<size_t>(b) * p.ld_ss + c] : 1.f;
-    sf[j] = p.shift ? p.shift[static_cast<size_t>(b) * p.ld_ss + c] : 0.f;
-    s1[j] = sS1[gi] * inv_n;
-    s2[j] = sS2[gi] * inv_n;
+  for (int j = 0; j < CH; ++j) {
+    const int gi = (cv * CH + j) / g.cpg;
+    const float s1 = sS1[gi] * inv_n, s2 = sS2[gi] * inv_n, rs = xa[j];
+    da[j] = rs * gam[j];
+    db[j] = -rs * s2 * xa[j];
+    dc[j] = -rs * (s1 + s2 * xc[j]);
   }
-  const int r0 = s * g.rows_per_cta, r1 = min(r0 + g.rows_per_cta, g.HW);
-  for (int r = r0 + lr; r < r1; r += g.nlanes) {
-    const size_t off = (static_cast<size_t>(b) * g.HW + r) * g.C + cv * 8;
-    float f[8], d[8];
-    load8(p.x, p.x_dtype, off, f);
-    load8(p.dy, PDDM_BF16, off, d);
+  for (int r = r0 + lr; r < r1; r += 4 * g.nlanes) {
+    float f[4][CH], d[4][CH];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xh = (f[j] - mu[j]) * rs[j];
-      const float z = (xh * ga[j] + be[j]) * sc[j] + sf[j];
-      float dz = d[j];
-      if (p.silu) {
-        const float sg = 1.f / (1.f + __expf(-z));
-        dz *= sg * (1.f + z * (1.f - sg));
+    for (int u = 0; u < 4; ++u)
+      if (r + u * g.nlanes < r1) {
+        const size_t off = base + static_cast<size_t>(r + u * g.nlanes) * g.C;
+        load4(p.x, p.x_dtype, off, f[u]);
+        load4(p.dx, p.dx_dtype, off, d[u]);
       }
-      f[j] = rs[j] * (ga[j] * dz * sc[j] - (s1[j] + xh * s2[j]));
-    }
-    store8(p.dx, p.dx_dtype, off, f);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (r + u * g.nlanes < r1) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) d[u][j] = d[u][j] * da[j] + f[u][j] * db[j] + dc[j];
+        store4(p.dx, p.dx_dtype, base + static_cast<size_t>(r + u * g.nlanes) * g.C, d[u]);
+      }
   }
 }
 
-// pass 3 (tiny): batch reductions and per-sample by-products from tot[b][5][C]
-__global__ void gn_bwd_finalize_kernel(pddm_gn_bwd_params p, const float* __restrict__ tot, GnGeom g) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// pass 3a (tiny): per-sample by-products from tot[b][5][C]; grid = (C/128, B)
+__global__ void gn_bwd_per_sample_kernel(pddm_gn_bwd_params p, const float* __restrict__ tot, GnGeom g) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
   if (c >= g.C) return;
   const int gi = c / g.cpg;
   const float inv_n = 1.f / (static_cast<float>(g.cpg) * g.HW);
-  const float gam = p.gamma[c];
-  float dg = 0.f, db = 0.f;
-  for (int b = 0; b < g.B; ++b) {
-    const float* t = tot + static_cast<size_t>(b) * 5 * g.C;
-    const float A = t[c], Bq = t[g.C + c];
-    dg += Bq;
-    db += A;
-    if (p.dx_colsum) {
-      float s1 = 0.f, s2 = 0.f;
-      for (int k = gi * g.cpg; k < (gi + 1) * g.cpg; ++k) {
-        s1 += p.gamma[k] * t[k];
-        s2 += p.gamma[k] * t[g.C + k];
-      }
-      p.dx_colsum[static_cast<size_t>(b) * g.C + c] =
-          p.rstd[b * g.G + gi] * (gam * A - (g.HW * s1 + s2 * t[2 * g.C + c]) * inv_n);
+  const float* t = tot + static_cast<size_t>(b) * 5 * g.C;
+  if (p.dx_colsum) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int k = gi * g.cpg; k < (gi + 1) * g.cpg; ++k) {
+      s1 += p.gamma[k] * t[k];
+      s2 += p.gamma[k] * t[g.C + k];
     }
-    if (p.dshift) p.dshift[static_cast<size_t>(b) * p.ld_ss + c] = t[3 * g.C + c];
-    if (p.dscale) p.dscale[static_cast<size_t>(b) * p.ld_ss + c] = t[4 * g.C + c];
+    p.dx_colsum[static_cast<size_t>(b) * g.C + c] =
+        p.rstd[b * g.G + gi] * (p.gamma[c] * t[c] - (g.HW * s1 + s2 * t[2 * g.C + c]) * inv_n);
   }
-  p.dgamma[c] = dg;
-  p.dbeta[c] = db;
+  if (p.dshift) p.dshift[static_cast<size_t>(b) * p.ld_ss + c] = t[3 * g.C + c];
+  if (p.dscale) p.dscale[static_cast<size_t>(b) * p.ld_ss + c] = t[4 * g.C + c];
+}
+// pass 3b (tiny): dgamma / dbeta = fixed-order sums over the batch; block = 32 channels x 8 batch lanes
+__global__ void gn_bwd_finalize_kernel(pddm_gn_bwd_params p, const float* __restrict__ tot, GnGeom g) {
+  __shared__ float sg[8][33], sb[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x, bl = threadIdx.y;
+  float dg = 0.f, db = 0.f;
+  if (c < g.C) {
+    for (int b = bl; b < g.B; b += 8) {
+      const float* t = tot + static_cast<size_t>(b) * 5 * g.C;
+      db += t[c];
+      dg += t[g.C + c];
+    }
+  }
+  sg[bl][threadIdx.x] = dg;
+  sb[bl][threadIdx.x] = db;
+  __syncthreads();
+  if (bl == 0 && c < g.C) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      dg += sg[k][threadIdx.x];
+      db += sb[k][threadIdx.x];
+    }
+    p.dgamma[c] = dg;
+    p.dbeta[c] = db;
+  }
 }
 
 static int make_geom(int B, int HW, int C, int G, GnGeom* g, int* threads) {
   if (B <= 0 || HW <= 0 || C <= 0 || G <= 0) return PDDM_ERR_BAD_ARG;
-  if (C % 8 || C % G || C / 8 > 512) return PDDM_ERR_UNSUPPORTED;
-  g->B = B; g->HW = HW; g->C = C; g->G = G; g->cpg = C / G; g->C8 = C / 8;
-  g->nlanes = 256 / g->C8 > 0 ? 256 / g->C8 : 1;
+  if (C % 8 || C % G || C / CH > 256) return PDDM_ERR_UNSUPPORTED;  // C <= 1024
+  g->B = B; g->HW = HW; g->C = C; g->G = G; g->cpg = C / G; g->CV = C / CH;
+  g->nlanes = 256 / g->CV > 0 ? 256 / g->CV : 1;
   if (g->nlanes > HW) g->nlanes = HW;
-  *threads = g->C8 * g->nlanes;
-  // split a sample over S CTAs so that ~2 waves of CTAs exist and each CTA still sees >= 4 rows per lane
+  *threads = g->CV * g->nlanes;
+  // cluster of S CTAs per sample (portable cluster sizes only): enough CTAs for ~4 per SM, >= 4 rows per lane
   const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
-  int S = (2 * sms + B - 1) / B;
-  const int max_s = HW / (g->nlanes * 4) > 0 ? HW / (g->nlanes * 4) : 1;
-  if (S > max_s) S = max_s;
-  if (S > kMaxSplit) S = kMaxSplit;
-  if (S < 1) S = 1;
+  int S = 1;
+  while (S < 8 && B * S < 4 * sms && HW / (2 * S) >= g->nlanes * 4) S *= 2;
   g->rows_per_cta = (HW + S - 1) / S;
-  g->S = (HW + g->rows_per_cta - 1) / g->rows_per_cta;
+  g->S = S;
+  if ((S - 1) * g->rows_per_cta >= HW) {  // keep every rank non-empty
+    g->S = 1;
+    g->rows_per_cta = HW;
+  }
   return PDDM_OK;
+}
+
+static int launch_cluster(const void* func, dim3 grid, int threads, size_t smem, int S, cudaStream_t s, void** args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = S;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelExC(&cfg, func, args) == cudaSuccess ? PDDM_OK : PDDM_ERR_CUDA;
 }
 
 }  // namespace pddm
 
 using namespace pddm;
 
-// scratch for the cross-CTA partial sums: forward B*S*G*2 floats, backward (B*S + B)*5*C floats (S <= 16)
+// Scratch queries.  The forward exchanges its partial sums through DSMEM and needs none (the argument is kept
+// so callers need not special-case it); the backward needs B*5*C floats for the per-sample channel totals.
 extern "C" size_t pddm_gn_silu_fwd_workspace(int32_t B, int32_t G) {
-  return static_cast<size_t>(B) * kMaxSplit * G * 2 * sizeof(float);
+  (void)B;
+  (void)G;
+  return 16;
 }
 extern "C" size_t pddm_gn_silu_bwd_workspace(int32_t B, int32_t C) {
-  return static_cast<size_t>(B) * (kMaxSplit + 1) * 5 * C * sizeof(float);
+  return static_cast<size_t>(B) * 5 * C * sizeof(float);
 }
 
 extern "C" int pddm_gn_silu_fwd(const pddm_gn_fwd_params* p, void* workspace, size_t workspace_bytes,
-                                   pddm_stream_t s_) {
+                                pddm_stream_t s_) {
   cudaStream_t s = static_cast<cudaStream_t>(s_);
-  if (!p || !p->x || !p->y || !p->gamma || !p->beta || !p->mean || !p->rstd || !workspace) return PDDM_ERR_BAD_ARG;
+  (void)workspace;
+  (void)workspace_bytes;
+  if (!p || !p->x || !p->y || !p->gamma || !p->beta || !p->mean || !p->rstd) return PDDM_ERR_BAD_ARG;
   if ((p->scale == nullptr) != (p->shift == nullptr)) return PDDM_ERR_BAD_ARG;
   GnGeom g;
   int threads;
   int rc = make_geom(p->B, p->HW, p->C, p->G, &g, &threads);
   if (rc) return rc;
   if (!aligned16(p->x) || !aligned16(p->y)) return PDDM_ERR_BAD_ARG;
-  if (workspace_bytes < static_cast<size_t>(g.B) * g.S * g.G * 2 * sizeof(float)) return PDDM_ERR_WORKSPACE;
-  float* part = static_cast<float*>(workspace);
-  dim3 grid(g.S, g.B);
-  gn_stats_kernel<<<grid, threads, 2 * g.nlanes * g.C * sizeof(float), s>>>(p->x, p->x_dtype, part, g);
-  if (cudaPeekAtLastError() != cudaSuccess) return PDDM_ERR_CUDA;
-  gn_apply_kernel<<<grid, threads, 2 * g.G * sizeof(float), s>>>(*p, part, g);
-  return launch_status();
+  const size_t smem = (2 * static_cast<size_t>(g.nlanes) * g.C + 4 * g.G) * sizeof(float);
+  pddm_gn_fwd_params pp = *p;
+  void* args[2] = {&pp, &g};
+  const bool ss = p->scale != nullptr;
+  const void* fn = p->silu ? (ss ? reinterpret_cast<const void*>(gn_fwd_cluster_kernel<true, true>)
+                                 : reinterpret_cast<const void*>(gn_fwd_cluster_kernel<true, false>))
+                           : (ss ? reinterpret_cast<const void*>(gn_fwd_cluster_kernel<false, true>)
+                                 : reinterpret_cast<const void*>(gn_fwd_cluster_kernel<false, false>));
+  rc = launch_cluster(fn, dim3(g.S, g.B), threads, smem, g.S, s, args);
+  return rc ? rc : launch_status();
 }
 
 extern "C" int pddm_gn_silu_bwd(const pddm_gn_bwd_params* p, void* workspace, size_t workspace_bytes,
@@ -369,15 +434,29 @@ extern "C" int pddm_gn_silu_bwd(const pddm_gn_bwd_params* p, void* workspace, si
   int rc = make_geom(p->B, p->HW, p->C, p->G, &g, &threads);
   if (rc) return rc;
   if (!aligned16(p->x) || !aligned16(p->dy) || !aligned16(p->dx)) return PDDM_ERR_BAD_ARG;
-  const size_t need = (static_cast<size_t>(g.B) * g.S + g.B) * 5 * g.C * sizeof(float);
+  const size_t need = static_cast<size_t>(g.B) * 5 * g.C * sizeof(float);
   if (workspace_bytes < need) return PDDM_ERR_WORKSPACE;
-  float* part = static_cast<float*>(workspace);
-  float* tot = part + static_cast<size_t>(g.B) * g.S * 5 * g.C;
-  dim3 grid(g.S, g.B);
-  gn_bwd_stats_kernel<<<grid, threads, 5 * g.nlanes * g.C * sizeof(float), s>>>(*p, part, g);
+  float* tot = static_cast<float*>(workspace);
+  const bool ss = p->scale != nullptr;
+  const int nq = ss ? 5 : 3;
+  const size_t smem = (nq * static_cast<size_t>(g.nlanes) * g.C + 7 * g.C + 2 * g.G) * sizeof(float);
+  const void* fn = p->silu ? (ss ? reinterpret_cast<const void*>(gn_bwd_cluster_kernel<true, true>)
+                                 : reinterpret_cast<const void*>(gn_bwd_cluster_kernel<true, false>))
+                           : (ss ? reinterpret_cast<const void*>(gn_bwd_cluster_kernel<false, true>)
+                                 : reinterpret_cast<const void*>(gn_bwd_cluster_kernel<false, false>));
+  if (smem > 48 * 1024) {
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+      return PDDM_ERR_UNSUPPORTED;
+  }
+  pddm_gn_bwd_params pp = *p;
+  void* args[3] = {&pp, &tot, &g};
+  rc = launch_cluster(fn, dim3(g.S, g.B), threads, smem, g.S, s, args);
+  if (rc) return rc;
   if (cudaPeekAtLastError() != cudaSuccess) return PDDM_ERR_CUDA;
-  gn_bwd_apply_kernel<<<grid, threads, (2 * g.C + 2 * g.G) * sizeof(float), s>>>(*p, part, tot, g);
-  if (cudaPeekAtLastError() != cudaSuccess) return PDDM_ERR_CUDA;
-  gn_bwd_finalize_kernel<<<(g.C + 127) / 128, 128, 0, s>>>(*p, tot, g);
+  if (p->dx_colsum || p->dshift || p->dscale) {
+    gn_bwd_per_sample_kernel<<<dim3((g.C + 127) / 128, g.B), 128, 0, s>>>(*p, tot, g);
+    if (cudaPeekAtLastError() != cudaSuccess) return PDDM_ERR_CUDA;
+  }
+  gn_bwd_finalize_kernel<<<(g.C + 31) / 32, dim3(32, 8), 0, s>>>(*p, tot, g);
   return launch_status();
 }

@@ -203,235 +203,78 @@ __global__ void colsum_kernel(const bf16* __restrict__ x, int ld, long long rows
 
 // ---------------------------------------------------------------------------------- weight packing
 __global__ void pack_w_kernel(const float* __restrict__ w, bf16* __restrict__ dst, int Cout, int Cin, int ntaps,
-                              int mode) {
-  const long long n = static_cast<long long>(Cout) * Cin * ntaps;
-  GRID_STRIDE(i, n) {  // i indexes dst
+                              int mode, int Cout_p, int Cin_p) {
+  const long long n = static_cast<long long>(Cout_p) * Cin_p * ntaps;
+  GRID_STRIDE(i, n) {  // i indexes dst (padded); padding rows / columns are written as zeros
     int co, ci, tap;
     if (mode == 0) {  // dst[co][tap][ci]
-      ci = static_cast<int>(i % Cin);
-      tap = static_cast<int>((i / Cin) % ntaps);
-      co = static_cast<int>(i / (static_cast<long long>(Cin) * ntaps));
+      ci = static_cast<int>(i % Cin_p);
+      tap = static_cast<int>((i / Cin_p) % ntaps);
+      co = static_cast<int>(i / (static_cast<long long>(Cin_p) * ntaps));
     } else {  // dst[ci][ntaps-1-tap][co]
-      co = static_cast<int>(i % Cout);
-      tap = ntaps - 1 - static_cast<int>((i / Cout) % ntaps);
-      ci = static_cast<int>(i / (static_cast<long long>(Cout) * ntaps));
+      co = static_cast<int>(i % Cout_p);
+      tap = ntaps - 1 - static_cast<int>((i / Cout_p) % ntaps);
+      ci = static_cast<int>(i / (static_cast<long long>(Cout_p) * ntaps));
     }
-    dst[i] = __float2bfloat16(w[(static_cast<long long>(co) * Cin + ci) * ntaps + tap]);
+    const float v = (co < Cout && ci < Cin) ? w[(static_cast<long long>(co) * Cin + ci) * ntaps + tap] : 0.f;
+    dst[i] = __float2bfloat16(v);
   }
 }
 
-// ---------------------------------------------------------------------------------- stem conv (Cin <= 4)
-// x: NCHW fp32 (the model input), y: NHWC bf16.  thread = (pixel, 8 output channels); weights in smem.
-__global__ void stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                                bf16* __restrict__ y, int B, int Cin, int H, int W, int Cout) {
-  extern __shared__ float sw[];  // [Cout][Cin*9] + bias[Cout]
-  const int K = Cin * 9;
-  for (int i = threadIdx.x; i < Cout * K; i += blockDim.x) sw[i] = w[i];
-  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[Cout * K + i] = bias ? bias[i] : 0.f;
-  __syncthreads();
-  const int C8 = Cout / 8;
-  const long long n = static_cast<long long>(B) * H * W * C8;
+// ---------------------------------------------------------------------------------- thin-conv helpers
+// The 3-channel stem and the 3/6-channel head are run on the tensor cores as well: the stem through an im2col of
+// the (tiny) model input to a [pixels, 32] bf16 patch matrix, the head by zero-padding its output channels.
+// out[b,h,w, ci*9 + tap] = x[b,ci,h+dh,w+dw]  (NCHW fp32 -> [B,H,W,Kp] bf16, zero outside the image and for k >= Cin*9)
+__global__ void im2col3x3_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B, int Cin, int H, int W,
+                                 int Kp) {
+  const int K8 = Kp / 8;
+  const long long n = static_cast<long long>(B) * H * W * K8;
   GRID_STRIDE(i, n) {
-    const int cg = static_cast<int>(i % C8);
-    long long r = i / C8;
+    const int kg = static_cast<int>(i % K8);
+    long long r = i / K8;
     const int xw = static_cast<int>(r % W); r /= W;
     const int yh = static_cast<int>(r % H);
     const int b = static_cast<int>(r / H);
-    float patch[36];
-    for (int ci = 0; ci < Cin; ++ci)
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int hh = yh + t / 3 - 1, ww = xw + t % 3 - 1;
-        patch[ci * 9 + t] = (hh >= 0 && hh < H && ww >= 0 && ww < W)
-                                ? __ldg(x + ((static_cast<size_t>(b) * Cin + ci) * H + hh) * W + ww)
-                                : 0.f;
-      }
-    float o[8];
+    float f[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int co = cg * 8 + j;
-      float acc = sw[Cout * K + co];
-      const float* wr = sw + co * K;
-      for (int k = 0; k < K; ++k) acc += patch[k] * wr[k];
-      o[j] = acc;
-    }
-    reinterpret_cast<uint4*>(y)[i] = pack8(o);
-  }
-}
-// dW[co][ci][tap] = sum_pix dY[pix][co] * X[b,ci,pix+tap] ; dbias[co] = sum dY.  thread = output channel.
-__global__ void stem_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ dw,
-                                  float* __restrict__ dbias, int B, int Cin, int H, int W, int Cout, int pix_per_block) {
-  extern __shared__ float sp[];  // [pix_per_block][Cin*9]
-  const int K = Cin * 9;
-  const long long npix = static_cast<long long>(B) * H * W;
-  const long long p0 = static_cast<long long>(blockIdx.x) * pix_per_block;
-  const int np = static_cast<int>(min(static_cast<long long>(pix_per_block), npix - p0));
-  for (int i = threadIdx.x; i < np * K; i += blockDim.x) {
-    const int pi = i / K, k = i - pi * K;
-    const int ci = k / 9, t = k - ci * 9;
-    const long long p = p0 + pi;
-    const int xw = static_cast<int>(p % W), yh = static_cast<int>((p / W) % H), b = static_cast<int>(p / (static_cast<long long>(W) * H));
-    const int hh = yh + t / 3 - 1, ww = xw + t % 3 - 1;
-    sp[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[((static_cast<size_t>(b) * Cin + ci) * H + hh) * W + ww] : 0.f;
-  }
-  __syncthreads();
-  for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
-    float acc[37];
-    for (int k = 0; k <= K; ++k) acc[k] = 0.f;
-    for (int pi = 0; pi < np; ++pi) {
-      const float g = __bfloat162float(dy[(p0 + pi) * Cout + co]);
-      const float* pr = sp + pi * K;
-      for (int k = 0; k < K; ++k) acc[k] += g * pr[k];
-      acc[K] += g;
-    }
-    for (int k = 0; k < K; ++k) atomicAdd(&dw[co * K + k], acc[k]);
-    if (dbias) atomicAdd(&dbias[co], acc[K]);
-  }
-}
-
-// ---------------------------------------------------------------------------------- head conv (Cout <= 8)
-// x: NHWC bf16, y: NCHW fp32 (the model output).  One warp per pixel; lane = 4-channel slice(s) of Cin.
-template <int COUT>
-__global__ void head_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                                float* __restrict__ y, int B, int Cin, int H, int W) {
-  extern __shared__ float sw[];  // [tap][co][Cin]
-  for (int i = threadIdx.x; i < 9 * COUT * Cin; i += blockDim.x) {
-    const int c = i % Cin, co = (i / Cin) % COUT, tap = i / (Cin * COUT);
-    sw[i] = w[(co * Cin + c) * 9 + tap];
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const long long warp_id = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
-  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  const long long npix = static_cast<long long>(B) * H * W;
-  for (long long p = warp_id; p < npix; p += nwarps) {
-    const int xw = static_cast<int>(p % W), yh = static_cast<int>((p / W) % H);
-    const int b = static_cast<int>(p / (static_cast<long long>(W) * H));
-    float acc[COUT];
-#pragma unroll
-    for (int j = 0; j < COUT; ++j) acc[j] = 0.f;
-    for (int t = 0; t < 9; ++t) {
+      const int k = kg * 8 + j;
+      const int ci = k / 9, t = k - ci * 9;
       const int hh = yh + t / 3 - 1, ww = xw + t % 3 - 1;
-      if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;  // warp-uniform
-      const bf16* xp = x + ((static_cast<size_t>(b) * H + hh) * W + ww) * Cin;
-      for (int c = lane * 4; c < Cin; c += 128) {
-        const uint2 v = *reinterpret_cast<const uint2*>(xp + c);
-        const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
-        const __nv_bfloat162 h1 = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
-        const float f0 = __low2float(h0), f1 = __high2float(h0), f2 = __low2float(h1), f3 = __high2float(h1);
-#pragma unroll
-        for (int j = 0; j < COUT; ++j) {
-          const float4 wv = *reinterpret_cast<const float4*>(sw + (t * COUT + j) * Cin + c);
-          acc[j] += f0 * wv.x + f1 * wv.y + f2 * wv.z + f3 * wv.w;
-        }
-      }
+      f[j] = (ci < Cin && hh >= 0 && hh < H && ww >= 0 && ww < W)
+                 ? __ldg(x + ((static_cast<size_t>(b) * Cin + ci) * H + hh) * W + ww)
+                 : 0.f;
     }
-#pragma unroll
-    for (int j = 0; j < COUT; ++j) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
-    }
-    if (lane < COUT) {
-      float v = 0.f;
-#pragma unroll
-      for (int j = 0; j < COUT; ++j)
-        if (lane == j) v = acc[j];
-      y[((static_cast<size_t>(b) * COUT + lane) * H + yh) * W + xw] = v + (bias ? bias[lane] : 0.f);
-    }
+    reinterpret_cast<uint4*>(out)[i] = pack8(f);
   }
 }
-// dX[pix][c] = sum_{tap,co} dY[b,co,pix-tap] * W[co][c][tap]
-template <int COUT>
-__global__ void head_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, bf16* __restrict__ dx, int B,
-                                  int Cin, int H, int W) {
-  extern __shared__ float sw[];  // [tap][co][Cin]
-  for (int i = threadIdx.x; i < 9 * COUT * Cin; i += blockDim.x) {
-    const int c = i % Cin, co = (i / Cin) % COUT, tap = i / (Cin * COUT);
-    sw[i] = w[(co * Cin + c) * 9 + tap];
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const long long warp_id = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
-  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  const long long npix = static_cast<long long>(B) * H * W;
-  for (long long p = warp_id; p < npix; p += nwarps) {
-    const int xw = static_cast<int>(p % W), yh = static_cast<int>((p / W) % H);
-    const int b = static_cast<int>(p / (static_cast<long long>(W) * H));
-    // lane i (and i + 32) fetches dY for (tap = i / COUT, co = i % COUT) at the source pixel of that tap
-    constexpr int NG = 9 * COUT;
-    float g0 = 0.f, g1 = 0.f;
+// NCHW fp32 [B,C,HW] -> NHWC bf16 [B,HW,Cp] with channels >= C zero (Cp % 8 == 0)
+__global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int B, int C, int HW,
+                                        int Cp) {
+  const int C8 = Cp / 8;
+  const long long n = static_cast<long long>(B) * HW * C8;
+  GRID_STRIDE(i, n) {
+    const int cg = static_cast<int>(i % C8);
+    const long long r = i / C8;
+    const int pix = static_cast<int>(r % HW), b = static_cast<int>(r / HW);
+    float f[8];
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int i = lane + 32 * half;
-      if (i < NG) {
-        const int t = i / COUT, co = i % COUT;
-        const int hh = yh - (t / 3 - 1), ww = xw - (t % 3 - 1);
-        float g = 0.f;
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W) g = dy[((static_cast<size_t>(b) * COUT + co) * H + hh) * W + ww];
-        if (half == 0) g0 = g; else g1 = g;
-      }
+    for (int j = 0; j < 8; ++j) {
+      const int c = cg * 8 + j;
+      f[j] = c < C ? __ldg(src + (static_cast<size_t>(b) * C + c) * HW + pix) : 0.f;
     }
-    for (int c0 = 0; c0 < Cin; c0 += 128) {  // uniform trip count: every lane takes part in the shuffles
-      const int c = c0 + lane * 4;
-      const bool active = c < Cin;
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-      for (int i = 0; i < NG; ++i) {
-        const float gi = i < 32 ? __shfl_sync(0xffffffffu, g0, i) : __shfl_sync(0xffffffffu, g1, i - 32);
-        if (active) {
-          const float4 wv = *reinterpret_cast<const float4*>(sw + i * Cin + c);  // i = tap*COUT + co
-          a0 += gi * wv.x; a1 += gi * wv.y; a2 += gi * wv.z; a3 += gi * wv.w;
-        }
-      }
-      if (active) {
-        uint2 o;
-        *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(a0, a1);
-        *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(a2, a3);
-        *reinterpret_cast<uint2*>(dx + p * Cin + c) = o;
-      }
-    }
+    reinterpret_cast<uint4*>(dst)[i] = pack8(f);
   }
 }
-// dW[co][c][tap] = sum_pix dY[b,co,pix] * X[pix+tap][c] ; thread = input channel c, block = pixel slab
-template <int COUT>
-__global__ void head_wgrad_kernel(const bf16* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
-                                  float* __restrict__ dbias, int B, int Cin, int H, int W, int pix_per_block) {
-  const long long npix = static_cast<long long>(B) * H * W;
-  const long long p0 = static_cast<long long>(blockIdx.x) * pix_per_block;
-  const long long p1 = min(p0 + pix_per_block, npix);
-  for (int c = threadIdx.x; c < Cin; c += blockDim.x) {
-    float acc[COUT * 9];
-    float bacc[COUT];
-#pragma unroll
-    for (int i = 0; i < COUT * 9; ++i) acc[i] = 0.f;
-#pragma unroll
-    for (int j = 0; j < COUT; ++j) bacc[j] = 0.f;
-    for (long long p = p0; p < p1; ++p) {
-      const int xw = static_cast<int>(p % W), yh = static_cast<int>((p / W) % H);
-      const int b = static_cast<int>(p / (static_cast<long long>(W) * H));
-      float g[COUT];
-#pragma unroll
-      for (int j = 0; j < COUT; ++j) {
-        g[j] = __ldg(dy + ((static_cast<size_t>(b) * COUT + j) * H + yh) * W + xw);
-        bacc[j] += g[j];
-      }
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int hh = yh + t / 3 - 1, ww = xw + t % 3 - 1;
-        if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-        const float xv = __bfloat162float(x[((static_cast<size_t>(b) * H + hh) * W + ww) * Cin + c]);
-#pragma unroll
-        for (int j = 0; j < COUT; ++j) acc[j * 9 + t] += g[j] * xv;
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < COUT; ++j)
-#pragma unroll
-      for (int t = 0; t < 9; ++t) atomicAdd(&dw[(j * Cin + c) * 9 + t], acc[j * 9 + t]);
-    if (c == 0 && dbias) {
-#pragma unroll
-      for (int j = 0; j < COUT; ++j) atomicAdd(&dbias[j], bacc[j]);
-    }
+// first C channels of NHWC fp32 [B,HW,ld] -> NCHW fp32 [B,C,HW]
+__global__ void nhwc_slice_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, int HW,
+                                          int ld) {
+  const long long n = static_cast<long long>(B) * C * HW;
+  GRID_STRIDE(i, n) {
+    const int pix = static_cast<int>(i % HW);
+    const long long r = i / HW;
+    const int c = static_cast<int>(r % C), b = static_cast<int>(r / C);
+    dst[i] = src[(static_cast<size_t>(b) * HW + pix) * ld + c];
   }
 }
 
@@ -557,98 +400,32 @@ extern "C" int pddm_colsum_per_sample(const void* x, int32_t B, int32_t HW, int3
   return colsum_launch(x, C, HW, B, C, out, C, 0, S(s));
 }
 extern "C" int pddm_pack_conv_weight(const float* w, void* dst, int32_t Cout, int32_t Cin, int32_t ntaps, int32_t mode,
-                                     pddm_stream_t s) {
-  if (!w || !dst || Cout <= 0 || Cin <= 0 || ntaps <= 0 || mode < 0 || mode > 1) return PDDM_ERR_BAD_ARG;
-  pack_w_kernel<<<grid_for(static_cast<long long>(Cout) * Cin * ntaps, 256), 256, 0, S(s)>>>(
-      w, static_cast<bf16*>(dst), Cout, Cin, ntaps, mode);
+                                     int32_t Cout_pad, int32_t Cin_pad, pddm_stream_t s) {
+  if (!w || !dst || Cout <= 0 || Cin <= 0 || ntaps <= 0 || mode < 0 || mode > 1 || Cout_pad < Cout || Cin_pad < Cin)
+    return PDDM_ERR_BAD_ARG;
+  pack_w_kernel<<<grid_for(static_cast<long long>(Cout_pad) * Cin_pad * ntaps, 256), 256, 0, S(s)>>>(
+      w, static_cast<bf16*>(dst), Cout, Cin, ntaps, mode, Cout_pad, Cin_pad);
   return launch_status();
 }
-
-extern "C" int pddm_stem_conv_fwd(const float* x, const float* w, const float* bias, void* y, int32_t B, int32_t Cin,
-                                  int32_t H, int32_t W, int32_t Cout, pddm_stream_t s) {
-  if (!x || !w || !y || B <= 0 || H <= 0 || W <= 0) return PDDM_ERR_BAD_ARG;
-  if (Cin < 1 || Cin > 4 || Cout % 8 || Cout > 1024) return PDDM_ERR_UNSUPPORTED;
-  const size_t smem = (static_cast<size_t>(Cout) * Cin * 9 + Cout) * sizeof(float);
-  stem_fwd_kernel<<<grid_for(static_cast<long long>(B) * H * W * (Cout / 8), 256), 256, smem, S(s)>>>(
-      x, w, bias, static_cast<bf16*>(y), B, Cin, H, W, Cout);
+extern "C" int pddm_im2col3x3(const float* x_nchw, void* out, int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t Kp,
+                              pddm_stream_t s) {
+  if (!x_nchw || !out || B <= 0 || Cin <= 0 || H <= 0 || W <= 0) return PDDM_ERR_BAD_ARG;
+  if (Kp % 8 || Kp < Cin * 9) return PDDM_ERR_UNSUPPORTED;
+  im2col3x3_kernel<<<grid_for(static_cast<long long>(B) * H * W * (Kp / 8), 256), 256, 0, S(s)>>>(
+      x_nchw, static_cast<bf16*>(out), B, Cin, H, W, Kp);
   return launch_status();
 }
-extern "C" int pddm_stem_conv_wgrad(const float* x, const void* dy, float* dw, float* dbias, int32_t B, int32_t Cin,
-                                    int32_t H, int32_t W, int32_t Cout, pddm_stream_t s) {
-  if (!x || !dy || !dw || B <= 0 || H <= 0 || W <= 0) return PDDM_ERR_BAD_ARG;
-  if (Cin < 1 || Cin > 4 || Cout > 1024) return PDDM_ERR_UNSUPPORTED;
-  if (cudaMemsetAsync(dw, 0, static_cast<size_t>(Cout) * Cin * 9 * sizeof(float), S(s)) != cudaSuccess) return PDDM_ERR_CUDA;
-  if (dbias && cudaMemsetAsync(dbias, 0, Cout * sizeof(float), S(s)) != cudaSuccess) return PDDM_ERR_CUDA;
-  const int ppb = 256;
-  const long long npix = static_cast<long long>(B) * H * W;
-  const int blocks = static_cast<int>((npix + ppb - 1) / ppb);
-  const int threads = Cout < 128 ? ((Cout + 31) / 32 * 32) : 128;
-  stem_wgrad_kernel<<<blocks, threads, static_cast<size_t>(ppb) * Cin * 9 * sizeof(float), S(s)>>>(
-      x, static_cast<const bf16*>(dy), dw, dbias, B, Cin, H, W, Cout, ppb);
+extern "C" int pddm_nchw_to_nhwc_padded(const float* src, void* dst, int32_t B, int32_t C, int32_t HW, int32_t Cp,
+                                        pddm_stream_t s) {
+  if (!src || !dst || B <= 0 || C <= 0 || HW <= 0) return PDDM_ERR_BAD_ARG;
+  if (Cp % 8 || Cp < C) return PDDM_ERR_UNSUPPORTED;
+  nchw_to_nhwc_pad_kernel<<<grid_for(static_cast<long long>(B) * HW * (Cp / 8), 256), 256, 0, S(s)>>>(
+      src, static_cast<bf16*>(dst), B, C, HW, Cp);
   return launch_status();
 }
-
-template <int COUT>
-static int head_fwd_t(const void* x, const float* w, const float* bias, float* y, int B, int Cin, int H, int W,
-                      cudaStream_t s) {
-  const size_t smem = static_cast<size_t>(9) * COUT * Cin * sizeof(float);
-  if (smem > 48 * 1024) {
-    if (cudaFuncSetAttribute(head_fwd_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) !=
-        cudaSuccess)
-      return PDDM_ERR_UNSUPPORTED;
-  }
-  head_fwd_kernel<COUT><<<grid_for(static_cast<long long>(B) * H * W * 4, 256), 256, smem, s>>>(
-      static_cast<const bf16*>(x), w, bias, y, B, Cin, H, W);
+extern "C" int pddm_nhwc_slice_to_nchw(const float* src, float* dst, int32_t B, int32_t C, int32_t HW, int32_t ld,
+                                       pddm_stream_t s) {
+  if (!src || !dst || B <= 0 || C <= 0 || HW <= 0 || ld < C) return PDDM_ERR_BAD_ARG;
+  nhwc_slice_to_nchw_kernel<<<grid_for(static_cast<long long>(B) * C * HW, 256), 256, 0, S(s)>>>(src, dst, B, C, HW, ld);
   return launch_status();
-}
-extern "C" int pddm_head_conv_fwd(const void* x, const float* w, const float* bias, float* y, int32_t B, int32_t Cin,
-                                  int32_t H, int32_t W, int32_t Cout, pddm_stream_t s) {
-  if (!x || !w || !y || B <= 0 || H <= 0 || W <= 0) return PDDM_ERR_BAD_ARG;
-  if (Cin % 4 || Cin > 1024) return PDDM_ERR_UNSUPPORTED;
-  switch (Cout) {
-    case 1: return head_fwd_t<1>(x, w, bias, y, B, Cin, H, W, S(s));
-    case 2: return head_fwd_t<2>(x, w, bias, y, B, Cin, H, W, S(s));
-    case 3: return head_fwd_t<3>(x, w, bias, y, B, Cin, H, W, S(s));
-    case 6: return head_fwd_t<6>(x, w, bias, y, B, Cin, H, W, S(s));
-    default: return PDDM_ERR_UNSUPPORTED;
-  }
-}
-template <int COUT>
-static int head_bwd_t(const void* x, const float* w, const float* dy, void* dx, float* dw, float* dbias, int B, int Cin,
-                      int H, int W, cudaStream_t s) {
-  const size_t smem = static_cast<size_t>(9) * COUT * Cin * sizeof(float);
-  if (dx) {
-    if (smem > 48 * 1024) {
-      if (cudaFuncSetAttribute(head_dgrad_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               static_cast<int>(smem)) != cudaSuccess)
-        return PDDM_ERR_UNSUPPORTED;
-    }
-    head_dgrad_kernel<COUT><<<grid_for(static_cast<long long>(B) * H * W * 4, 256), 256, smem, s>>>(
-        dy, w, static_cast<bf16*>(dx), B, Cin, H, W);
-    if (cudaPeekAtLastError() != cudaSuccess) return PDDM_ERR_CUDA;
-  }
-  if (dw) {
-    if (cudaMemsetAsync(dw, 0, static_cast<size_t>(COUT) * Cin * 9 * sizeof(float), s) != cudaSuccess) return PDDM_ERR_CUDA;
-    if (dbias && cudaMemsetAsync(dbias, 0, COUT * sizeof(float), s) != cudaSuccess) return PDDM_ERR_CUDA;
-    const long long npix = static_cast<long long>(B) * H * W;
-    int blocks = 4 * (device_info().sm_count > 0 ? device_info().sm_count : 148);
-    int ppb = static_cast<int>((npix + blocks - 1) / blocks);
-    if (ppb < 16) ppb = 16;
-    blocks = static_cast<int>((npix + ppb - 1) / ppb);
-    const int threads = Cin < 128 ? ((Cin + 31) / 32 * 32) : 128;
-    head_wgrad_kernel<COUT><<<blocks, threads, 0, s>>>(static_cast<const bf16*>(x), dy, dw, dbias, B, Cin, H, W, ppb);
-  }
-  return launch_status();
-}
-extern "C" int pddm_head_conv_bwd(const void* x, const float* w, const float* dy, void* dx, float* dw, float* dbias,
-                                  int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t Cout, pddm_stream_t s) {
-  if (!x || !w || !dy || B <= 0 || H <= 0 || W <= 0) return PDDM_ERR_BAD_ARG;
-  if (Cin % 4 || Cin > 1024) return PDDM_ERR_UNSUPPORTED;
-  switch (Cout) {
-    case 1: return head_bwd_t<1>(x, w, dy, dx, dw, dbias, B, Cin, H, W, S(s));
-    case 2: return head_bwd_t<2>(x, w, dy, dx, dw, dbias, B, Cin, H, W, S(s));
-    case 3: return head_bwd_t<3>(x, w, dy, dx, dw, dbias, B, Cin, H, W, S(s));
-    case 6: return head_bwd_t<6>(x, w, dy, dx, dw, dbias, B, Cin, H, W, S(s));
-    default: return PDDM_ERR_UNSUPPORTED;
-  }
 }

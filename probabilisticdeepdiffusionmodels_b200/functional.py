@@ -65,14 +65,16 @@ def _fill_taps(p, taps):
 
 
 # ------------------------------------------------------------------------------------------ conv / linear
-def pack_weight(w, mode):
-    """fp32 [Cout, Cin, *k] -> bf16 GEMM operand.  mode 0: [Cout, taps, Cin]; mode 1 (dgrad): [Cin, taps(flipped), Cout]."""
+def pack_weight(w, mode, cout_pad=None, cin_pad=None):
+    """fp32 [Cout, Cin, *k] -> bf16 GEMM operand (optionally zero-padded).
+    mode 0: [Cout_pad, taps, Cin_pad]; mode 1 (dgrad): [Cin_pad, taps(flipped), Cout_pad]."""
     L.require_device(w)
     _chk(w, f32)
     cout, cin = w.shape[0], w.shape[1]
     ntaps = w.numel() // (cout * cin)
-    dst = torch.empty((cout, ntaps, cin) if mode == 0 else (cin, ntaps, cout), dtype=bf16, device=w.device)
-    L.call("pddm_pack_conv_weight", L.ptr(w), L.ptr(dst), cout, cin, ntaps, mode, L.stream())
+    cop, cip = cout_pad or cout, cin_pad or cin
+    dst = torch.empty((cop, ntaps, cip) if mode == 0 else (cip, ntaps, cop), dtype=bf16, device=w.device)
+    L.call("pddm_pack_conv_weight", L.ptr(w), L.ptr(dst), cout, cin, ntaps, mode, cop, cip, L.stream())
     return dst
 
 
@@ -333,43 +335,63 @@ def attn_bwd(qkv, out, dout, lse, heads):
 
 
 # ------------------------------------------------------------------------------------------ thin convs
-def stem_conv_fwd(x_nchw, w, bias):
+def _pad32(n):
+    return (n + 31) // 32 * 32
+
+
+def im2col3x3(x_nchw):
+    """NCHW fp32 model input -> [B, H, W, Kp] bf16 patch matrix (k = ci*9 + tap, Kp = Cin*9 rounded up to 32)."""
     L.require_device(x_nchw)
     _chk(x_nchw, f32)
     B, Cin, H, W = x_nchw.shape
-    y = torch.empty((B, H, W, w.shape[0]), dtype=bf16, device=x_nchw.device)
-    L.call("pddm_stem_conv_fwd", L.ptr(x_nchw), L.ptr(_chk(w, f32)), L.ptr(bias), L.ptr(y), B, Cin, H, W, w.shape[0],
-           L.stream())
-    return y
+    Kp = _pad32(Cin * 9)
+    out = torch.empty((B, H, W, Kp), dtype=bf16, device=x_nchw.device)
+    L.call("pddm_im2col3x3", L.ptr(x_nchw), L.ptr(out), B, Cin, H, W, Kp, L.stream())
+    return out
 
 
-def stem_conv_wgrad(x_nchw, dy, w_shape):
-    B, Cin, H, W = x_nchw.shape
-    dw = torch.empty(w_shape, dtype=f32, device=dy.device)
-    db = torch.empty(w_shape[0], dtype=f32, device=dy.device)
-    L.call("pddm_stem_conv_wgrad", L.ptr(x_nchw), L.ptr(_chk(dy, bf16)), L.ptr(dw), L.ptr(db), B, Cin, H, W,
-           w_shape[0], L.stream())
-    return dw, db
+def stem_conv_fwd(x_nchw, w, bias):
+    """conv3x3(Cin<=4) as a K=32 tensor-core GEMM over the im2col patches -> (y NHWC bf16, patches)."""
+    patches = im2col3x3(x_nchw)
+    B, H, W, Kp = patches.shape
+    cout = w.shape[0]
+    wp = pack_weight(w.view(cout, -1, 1), 0, cin_pad=Kp)  # [Cout, 1, Kp]
+    return tap_gemm(patches, wp, taps_1x1(), B, H, W, bias=bias), patches
+
+
+def stem_conv_wgrad(patches, dy, w_shape):
+    B, H, W, Kp = patches.shape
+    cout, k = w_shape[0], w_shape[1] * 9
+    dwp = tap_wgrad(patches, dy, taps_1x1(), B, H, W, Kp, cout, (cout, Kp, 1))
+    return dwp.view(cout, Kp)[:, :k].reshape(w_shape), colsum(dy, cout)
 
 
 def head_conv_fwd(x, w, bias):
+    """conv3x3 to Cout<=8 channels with the output channels zero-padded to 8; result NCHW fp32."""
     L.require_device(x)
     _chk(x, bf16)
     B, H, W, Cin = x.shape
-    y = torch.empty((B, w.shape[0], H, W), dtype=f32, device=x.device)
-    L.call("pddm_head_conv_fwd", L.ptr(x), L.ptr(_chk(w, f32)), L.ptr(bias), L.ptr(y), B, Cin, H, W, w.shape[0],
-           L.stream())
+    cout = w.shape[0]
+    wp = pack_weight(w, 0, cout_pad=8)
+    bias_p = None
+    if bias is not None:
+        bias_p = torch.zeros(8, dtype=f32, device=x.device)
+        bias_p[:cout].copy_(bias)
+    y8 = tap_gemm(x, wp, taps_3x3(), B, H, W, bias=bias_p, out_dtype=f32)
+    y = torch.empty((B, cout, H, W), dtype=f32, device=x.device)
+    L.call("pddm_nhwc_slice_to_nchw", L.ptr(y8), L.ptr(y), B, cout, H * W, 8, L.stream())
     return y
 
 
 def head_conv_bwd(x, w, dy_nchw):
     B, H, W, Cin = x.shape
-    dx = torch.empty_like(x)
-    dw = torch.empty(w.shape, dtype=f32, device=x.device)
-    db = torch.empty(w.shape[0], dtype=f32, device=x.device)
-    L.call("pddm_head_conv_bwd", L.ptr(x), L.ptr(w), L.ptr(_chk(dy_nchw, f32)), L.ptr(dx), L.ptr(dw), L.ptr(db), B, Cin,
-           H, W, w.shape[0], L.stream())
-    return dx, dw, db
+    cout = w.shape[0]
+    dyp = torch.empty((B, H, W, 32), dtype=bf16, device=x.device)
+    L.call("pddm_nchw_to_nhwc_padded", L.ptr(_chk(dy_nchw, f32)), L.ptr(dyp), B, cout, H * W, 32, L.stream())
+    wp1 = pack_weight(w, 1, cout_pad=32)  # [Cin, 9, 32]
+    dx = tap_gemm(dyp, wp1, taps_3x3(), B, H, W)
+    dw32 = tap_wgrad(x, dyp, taps_3x3(), B, H, W, Cin, 32, (32, Cin, 3, 3))
+    return dx, dw32[:cout].contiguous(), colsum(dyp, 32)[:cout].contiguous()
 
 
 # ------------------------------------------------------------------------------------------ diffusion math

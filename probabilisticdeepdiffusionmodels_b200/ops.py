@@ -152,7 +152,28 @@ def _conv_backward(ctx, dy, _daux):
     stride, upsample, in_h, in_w = ctx.meta
     need_dx, need_db, need_dbc, need_dres = ctx.needs
     dy = dy.contiguous()
-    dx, dw, db, dbc = torch.ops.pddm.conv2d_bwd(dy, xin, weight, stride, upsample, in_h, in_w, need_dx, need_db, need_dbc)
+    # Column sums of dy may already exist: the GroupNorm backward that produced dy emits sum_hw(dx) per sample as
+    # a by-product (attribute on the gradient tensor), and sibling convs sharing dy share its bias sum.
+    # (the stamps guard against autograd accumulating another gradient into the same tensor in place)
+    per_sample = bias_sum = None
+    st = getattr(dy, "_pddm_colsum", None)
+    if st is not None and st[1] == dy._version:
+        per_sample = st[0]
+    st = getattr(dy, "_pddm_bias_sum", None)
+    if st is not None and st[1] == dy._version:
+        bias_sum = st[0]
+    if per_sample is not None and bias_sum is None and need_db:
+        bias_sum = per_sample.sum(0)
+    want_db = need_db and bias_sum is None
+    want_dbc = need_dbc and per_sample is None
+    dx, dw, db, dbc = torch.ops.pddm.conv2d_bwd(dy, xin, weight, stride, upsample, in_h, in_w, need_dx, want_db, want_dbc)
+    if need_db:
+        if want_db:
+            dy._pddm_bias_sum = (db, dy._version)
+        else:
+            db = bias_sum
+    if need_dbc and not want_dbc:
+        dbc = per_sample
     return (dx if need_dx else None, dw, db if need_db else None, dbc if need_dbc else None,
             dy if need_dres else None, None, None)
 
@@ -290,16 +311,20 @@ def _(x, gamma, beta, scale, shift, groups, eps, silu):
 
 @torch.library.custom_op("pddm::gn_silu_bwd", mutates_args=())
 def gn_silu_bwd(x: Tensor, dy: Tensor, gamma: Tensor, beta: Tensor, scale: Optional[Tensor], shift: Optional[Tensor],
-                mean: Tensor, rstd: Tensor, groups: int, silu: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
-    dx, dg, db, _, dsc, dsh = F.gn_silu_bwd(x, dy, gamma, beta, mean, rstd, groups, silu, scale, shift, dx_dtype=x.dtype)
-    return dx, dg, db, dsc if dsc is not None else _empty(x), dsh if dsh is not None else _empty(x)
+                mean: Tensor, rstd: Tensor, groups: int, silu: bool
+                ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """-> (dx, dgamma, dbeta, dscale, dshift, sum_hw(dx) [B, C])"""
+    dx, dg, db, cs, dsc, dsh = F.gn_silu_bwd(x, dy, gamma, beta, mean, rstd, groups, silu, scale, shift,
+                                             dx_dtype=x.dtype, want_colsum=True)
+    return dx, dg, db, dsc if dsc is not None else _empty(x), dsh if dsh is not None else _empty(x), cs
 
 
 @gn_silu_bwd.register_fake
 def _(x, dy, gamma, beta, scale, shift, mean, rstd, groups, silu):
     e = x.new_empty((0,), dtype=f32)
     ss = x.new_empty(scale.shape, dtype=f32) if scale is not None else e
-    return x.new_empty(x.shape), gamma.new_empty(gamma.shape), gamma.new_empty(gamma.shape), ss, ss
+    return (x.new_empty(x.shape), gamma.new_empty(gamma.shape), gamma.new_empty(gamma.shape), ss, ss,
+            x.new_empty((x.shape[0], x.shape[-1]), dtype=f32))
 
 
 def _gn_setup(ctx, inputs, output):
@@ -316,7 +341,9 @@ def _gn_backward(ctx, dy, _dm, _dr):
     else:
         x, gamma, beta, mean, rstd = ctx.saved_tensors
         scale = shift = None
-    dx, dg, db, dsc, dsh = torch.ops.pddm.gn_silu_bwd(x, dy.contiguous(), gamma, beta, scale, shift, mean, rstd, groups, silu)
+    dx, dg, db, dsc, dsh, cs = torch.ops.pddm.gn_silu_bwd(x, dy.contiguous(), gamma, beta, scale, shift, mean, rstd,
+                                                          groups, silu)
+    dx._pddm_colsum = (cs, dx._version)  # consumed by the backward of the conv that produced x (bias / timestep-embedding grads)
     return dx, dg, db, (dsc if has_ss else None), (dsh if has_ss else None), None, None, None
 
 
@@ -402,34 +429,36 @@ torch.library.register_autograd("pddm::add", lambda ctx, g: (g, g))
 
 # ================================================================================================ stem / head
 @torch.library.custom_op("pddm::stem_conv", mutates_args=())
-def stem_conv(x: Tensor, weight: Tensor, bias: Tensor) -> Tensor:
-    """First conv (Cin <= 4): NCHW fp32 model input -> NHWC bf16 (src/modules/unet.py:353)."""
+def stem_conv(x: Tensor, weight: Tensor, bias: Tensor) -> Tuple[Tensor, Tensor]:
+    """First conv (Cin <= 4): NCHW fp32 model input -> NHWC bf16 (src/modules/unet.py:353); also returns the im2col
+    patch matrix the tensor-core GEMM read (needed by the weight gradient)."""
     return F.stem_conv_fwd(x, weight, bias)
 
 
 @stem_conv.register_fake
 def _(x, weight, bias):
-    return x.new_empty((x.shape[0], x.shape[2], x.shape[3], weight.shape[0]), dtype=bf16)
+    B, Cin, H, W = x.shape
+    return x.new_empty((B, H, W, weight.shape[0]), dtype=bf16), x.new_empty((B, H, W, (Cin * 9 + 31) // 32 * 32), dtype=bf16)
 
 
 @torch.library.custom_op("pddm::stem_conv_bwd", mutates_args=())
-def stem_conv_bwd(x: Tensor, dy: Tensor, weight: Tensor) -> Tuple[Tensor, Tensor]:
-    return F.stem_conv_wgrad(x, dy, tuple(weight.shape))
+def stem_conv_bwd(patches: Tensor, dy: Tensor, weight: Tensor) -> Tuple[Tensor, Tensor]:
+    return F.stem_conv_wgrad(patches, dy, tuple(weight.shape))
 
 
 @stem_conv_bwd.register_fake
-def _(x, dy, weight):
+def _(patches, dy, weight):
     return weight.new_empty(weight.shape), weight.new_empty((weight.shape[0],))
 
 
-def _stem_backward(ctx, dy):
-    x, w = ctx.saved_tensors
-    dw, db = torch.ops.pddm.stem_conv_bwd(x, dy.contiguous(), w)
+def _stem_backward(ctx, dy, _dp):
+    patches, w = ctx.saved_tensors
+    dw, db = torch.ops.pddm.stem_conv_bwd(patches, dy.contiguous(), w)
     return None, dw, db  # the model input needs no gradient (x_t is data)
 
 
 torch.library.register_autograd("pddm::stem_conv", _stem_backward,
-                                setup_context=lambda ctx, inputs, output: ctx.save_for_backward(inputs[0], inputs[1]))
+                                setup_context=lambda ctx, inputs, output: ctx.save_for_backward(output[1], inputs[1]))
 
 
 @torch.library.custom_op("pddm::head_conv", mutates_args=())

@@ -269,7 +269,7 @@ class UNetModel(nn.Module):
 
         stem = self.input_blocks[0][0]
         if self.in_channels <= 4:
-            h = P.stem_conv(x, stem.weight, stem.bias)
+            h = P.stem_conv(x, stem.weight, stem.bias)[0]
         else:
             h = _conv(P.to_nhwc(x), stem)
         hs = [h]
@@ -281,7 +281,7 @@ class UNetModel(nn.Module):
             h = module(P.concat_channels(h, hs.pop()), emb)
         h = _gn(h, self.out[0], True)
         head = self.out[2]
-        if self.out_channels in (1, 2, 3, 6):
+        if self.out_channels <= 8:
             out = P.head_conv(h, head.weight, head.bias)
         else:
             out = P.to_nchw(_conv(h, head))
@@ -293,7 +293,7 @@ class UNetModel(nn.Module):
         result = dict(down=[], up=[])
         x = x.float().contiguous()
         stem = self.input_blocks[0][0]
-        h = P.stem_conv(x, stem.weight, stem.bias) if self.in_channels <= 4 else _conv(P.to_nhwc(x), stem)
+        h = P.stem_conv(x, stem.weight, stem.bias)[0] if self.in_channels <= 4 else _conv(P.to_nhwc(x), stem)
         hs = [h]
         result["down"].append(P.to_nchw(h))
         for module in list(self.input_blocks)[1:]:

@@ -99,8 +99,17 @@ def test_nll_eval_matches_reference(golden, mode, monkeypatch):
         nll = eng.calculate_likelihood(T(g["x0"]).cuda())
     assert abs(nll["L_T"].item() - float(g[f"{mode}_nll20_LT"])) <= 1e-5 * abs(float(g[f"{mode}_nll20_LT"])) + 1e-9
     assert abs(nll["L_0"].item() - float(g[f"{mode}_nll20_L0"])) < 2e-2 * abs(float(g[f"{mode}_nll20_L0"])) + 1e-3
-    np.testing.assert_allclose(nll["L_intermediate"].cpu().numpy(), g[f"{mode}_nll20_Lint"], rtol=3e-2)
-    assert abs(nll["nll"].item() - float(g[f"{mode}_nll20_nll"])) <= 2e-2 * abs(float(g[f"{mode}_nll20_nll"])) + 1e-3
+    want = g[f"{mode}_nll20_Lint"]
+    got = nll["L_intermediate"].cpu().numpy()
+    # with T=20 the linear schedule makes q(x_19|x_20,x_0) degenerate (posterior variance underflows): the reference
+    # itself reports inf there, and so must we
+    assert np.array_equal(np.isinf(got), np.isinf(want))
+    np.testing.assert_allclose(got[np.isfinite(want)], want[np.isfinite(want)], rtol=3e-2)
+    ref_nll = float(g[f"{mode}_nll20_nll"])
+    if np.isfinite(ref_nll):
+        assert abs(nll["nll"].item() - ref_nll) <= 2e-2 * abs(ref_nll) + 1e-3
+    else:
+        assert not np.isfinite(nll["nll"].item())
 
 
 def test_hybrid_loss_learned_sigma(golden):

@@ -166,10 +166,11 @@ def test_stem_head_convs(P):
         yr = TF.conv2d(x, wr, br, padding=1)
         yr.backward(gy)
         wd, bd = w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
-        y = P.stem_conv(x.cuda(), wd, bd)
+        y, _ = P.stem_conv(x.cuda(), wd, bd)
         y.backward(nhwc(gy))
-        assert rel(nchw(y), yr.detach()) < 4e-3
-        assert rel(wd.grad, wr.grad) < 1e-4 and rel(bd.grad, br.grad) < 1e-4
+        # stem: the fp32 model input and weights are rounded to bf16 for the tensor-core GEMM
+        assert rel(nchw(y), yr.detach()) < 6e-3
+        assert rel(wd.grad, wr.grad) < 5e-3 and rel(bd.grad, br.grad) < 1e-4
     for Cin, Cout, H in [(128, 3, 32), (32, 1, 28), (128, 6, 16), (32, 2, 28)]:
         x = rnd(2, Cin, H, H, seed=1).to(bf16).float()
         w, b = rnd(Cout, Cin, 3, 3, seed=2) * 0.05, rnd(Cout, seed=3)
@@ -181,9 +182,10 @@ def test_stem_head_convs(P):
         wd, bd = w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
         y = P.head_conv(xd, wd, bd)
         y.backward(gy.cuda())
-        assert rel(y, yr.detach()) < 1e-5
-        assert rel(nchw(xd.grad), xr.grad) < 4e-3
-        assert rel(wd.grad, wr.grad) < 1e-4 and rel(bd.grad, br.grad) < 1e-4
+        # head: bf16 weights/inputs on the tensor cores, fp32 output; dy is rounded to bf16 for the gradient GEMMs
+        assert rel(y, yr.detach()) < 4e-3
+        assert rel(nchw(xd.grad), xr.grad) < 8e-3
+        assert rel(wd.grad, wr.grad) < 5e-3 and rel(bd.grad, br.grad) < 5e-3
 
 
 def test_layout_and_small_ops(P):
