@@ -194,10 +194,8 @@ def main():
     x_dev = host_x.to(dev)
     hook = parallel.FlatGradAllReduce() if world > 1 else None
 
-    launches0 = _lib.KERNELS[0]
     step = eng.capture_train_step((B, 3, RES, RES), grad_hook=hook)
-    # capture_train_step ran 3 eager warm-ups + 1 capture: kernels per step = delta / 4
-    kernels_per_step = (_lib.KERNELS[0] - launches0) // 4
+    kernels_per_step = step.state["kernels_per_step"]  # this library's kernels inside one captured step
 
     def barrier():
         if world > 1:

@@ -290,6 +290,19 @@ int pddm_conv2d_wgrad(const pddm_wgrad_params* p, void* workspace, size_t worksp
 int pddm_pack_conv_weight(const float* w, void* dst, int32_t Cout, int32_t Cin, int32_t ntaps, int32_t mode,
                           int32_t Cout_pad, int32_t Cin_pad, pddm_stream_t stream);
 
+/* Re-pack every weight of a model in ONE launch (after each optimiser step).  descs: device array of
+ * pddm_pack_desc; blocks: device array of int32 pairs (descriptor index, first destination element) -- one
+ * thread block packs PDDM_PACK_CHUNK consecutive destination elements of one tensor. */
+#define PDDM_PACK_CHUNK 4096
+typedef struct {
+  const float* src;
+  void* dst; /* bf16 */
+  int32_t Cout, Cin, ntaps, mode, Cout_pad, Cin_pad;
+} pddm_pack_desc;
+int pddm_pack_weights_multi(const void* descs, const void* blocks, int32_t nblocks, pddm_stream_t stream);
+/* out[c] = sum_m x[m, c] for a small fp32 matrix [M, C] (deterministic). */
+int pddm_colsum_f32(const float* x, int32_t M, int32_t C, float* out, pddm_stream_t stream);
+
 /* Helpers that put the two "thin" convolutions on the tensor cores as well: the stem conv (Cin <= 4, reads the
  * NCHW fp32 model input, src/modules/unet.py:353) becomes a K=32 GEMM over an im2col patch matrix, and the head conv
  * (Cout <= 8, writes the NCHW fp32 model output, src/modules/unet.py:440) runs with zero-padded output channels.

@@ -79,6 +79,14 @@ class WgradParams(C.Structure):
                 ("dw_layout", c_i32), ("accumulate", c_i32)]
 
 
+class PackDesc(C.Structure):
+    _fields_ = [("src", c_vp), ("dst", c_vp), ("Cout", c_i32), ("Cin", c_i32), ("ntaps", c_i32), ("mode", c_i32),
+                ("Cout_pad", c_i32), ("Cin_pad", c_i32)]
+
+
+PACK_CHUNK = 4096
+
+
 class AttnFwdParams(C.Structure):
     _fields_ = [("qkv", c_vp), ("out", c_vp), ("lse", c_vp), ("B", c_i32), ("T", c_i32), ("heads", c_i32), ("d", c_i32)]
 
@@ -128,6 +136,8 @@ SIGNATURES = {
     "pddm_conv2d_wgrad_workspace": (c_sz, [P(WgradParams)]),
     "pddm_conv2d_wgrad": (c_i32, [P(WgradParams), c_vp, c_sz, c_vp]),
     "pddm_pack_conv_weight": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "pddm_pack_weights_multi": (c_i32, [c_vp, c_vp, c_i32, c_vp]),
+    "pddm_colsum_f32": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp]),
     "pddm_im2col3x3": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "pddm_nchw_to_nhwc_padded": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "pddm_nhwc_slice_to_nchw": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),

@@ -71,13 +71,13 @@ __global__ void __launch_bounds__(256, 4) gn_fwd_cluster_kernel(pddm_gn_fwd_para
   float sum[CH], sq[CH];
 #pragma unroll
   for (int j = 0; j < CH; ++j) sum[j] = sq[j] = 0.f;
-  for (int r = r0 + lr; r < r1; r += 4 * g.nlanes) {  // 4 independent vector loads in flight per thread
-    float f[4][CH];
+  for (int r = r0 + lr; r < r1; r += 8 * g.nlanes) {  // 8 independent vector loads in flight per thread
+    float f[8][CH];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < 8; ++u)
       if (r + u * g.nlanes < r1) load4(p.x, p.x_dtype, base + static_cast<size_t>(r + u * g.nlanes) * g.C, f[u]);
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < 8; ++u)
       if (r + u * g.nlanes < r1) {
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
@@ -142,13 +142,13 @@ __global__ void __launch_bounds__(256, 4) gn_fwd_cluster_kernel(pddm_gn_fwd_para
     ca[j] = a;
     cc[j] = o;
   }
-  for (int r = r0 + lr; r < r1; r += 4 * g.nlanes) {
-    float f[4][CH];
+  for (int r = r0 + lr; r < r1; r += 8 * g.nlanes) {
+    float f[8][CH];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < 8; ++u)
       if (r + u * g.nlanes < r1) load4(p.x, p.x_dtype, base + static_cast<size_t>(r + u * g.nlanes) * g.C, f[u]);
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < 8; ++u)
       if (r + u * g.nlanes < r1) {
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
@@ -200,17 +200,17 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_cluster_kernel(pddm_gn_bwd_para
     for (int q = 0; q < NQ; ++q) acc[q][j] = 0.f;
   }
   const int r0 = s * g.rows_per_cta, r1 = min(r0 + g.rows_per_cta, g.HW);
-  for (int r = r0 + lr; r < r1; r += 2 * g.nlanes) {
-    float f[2][CH], d[2][CH];
+  for (int r = r0 + lr; r < r1; r += 4 * g.nlanes) {
+    float f[4][CH], d[4][CH];
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+    for (int u = 0; u < 4; ++u)
       if (r + u * g.nlanes < r1) {
         const size_t off = base + static_cast<size_t>(r + u * g.nlanes) * g.C;
         load4(p.x, p.x_dtype, off, f[u]);
         load4(p.dy, PDDM_BF16, off, d[u]);
       }
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+    for (int u = 0; u < 4; ++u)
       if (r + u * g.nlanes < r1) {
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
@@ -320,13 +320,14 @@ __global__ void gn_bwd_per_sample_kernel(pddm_gn_bwd_params p, const float* __re
   if (p.dshift) p.dshift[static_cast<size_t>(b) * p.ld_ss + c] = t[3 * g.C + c];
   if (p.dscale) p.dscale[static_cast<size_t>(b) * p.ld_ss + c] = t[4 * g.C + c];
 }
-// pass 3b (tiny): dgamma / dbeta = fixed-order sums over the batch; block = 32 channels x 8 batch lanes
+// pass 3b (tiny): dgamma / dbeta = fixed-order sums over the batch; block = 32 channels x 32 batch lanes
 __global__ void gn_bwd_finalize_kernel(pddm_gn_bwd_params p, const float* __restrict__ tot, GnGeom g) {
-  __shared__ float sg[8][33], sb[8][33];
+  __shared__ float sg[32][33], sb[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x, bl = threadIdx.y;
   float dg = 0.f, db = 0.f;
   if (c < g.C) {
-    for (int b = bl; b < g.B; b += 8) {
+#pragma unroll 4
+    for (int b = bl; b < g.B; b += 32) {
       const float* t = tot + static_cast<size_t>(b) * 5 * g.C;
       db += t[c];
       dg += t[g.C + c];
@@ -337,7 +338,7 @@ __global__ void gn_bwd_finalize_kernel(pddm_gn_bwd_params p, const float* __rest
   __syncthreads();
   if (bl == 0 && c < g.C) {
 #pragma unroll
-    for (int k = 1; k < 8; ++k) {
+    for (int k = 1; k < 32; ++k) {
       dg += sg[k][threadIdx.x];
       db += sb[k][threadIdx.x];
     }
@@ -457,6 +458,6 @@ extern "C" int pddm_gn_silu_bwd(const pddm_gn_bwd_params* p, void* workspace, si
     gn_bwd_per_sample_kernel<<<dim3((g.C + 127) / 128, g.B), 128, 0, s>>>(*p, tot, g);
     if (cudaPeekAtLastError() != cudaSuccess) return PDDM_ERR_CUDA;
   }
-  gn_bwd_finalize_kernel<<<(g.C + 31) / 32, dim3(32, 8), 0, s>>>(*p, tot, g);
+  gn_bwd_finalize_kernel<<<(g.C + 31) / 32, dim3(32, 32), 0, s>>>(*p, tot, g);
   return launch_status();
 }

@@ -183,12 +183,20 @@ __global__ void colsum_kernel(const bf16* __restrict__ x, int ld, long long rows
   const int cv = threadIdx.x % C8, lane_r = threadIdx.x / C8, nlanes = blockDim.x / C8;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (lane_r < nlanes) {
-    for (long long r = static_cast<long long>(blockIdx.x) * nlanes + lane_r; r < rows_per_seg;
-         r += static_cast<long long>(gridDim.x) * nlanes) {
-      float f[8];
-      unpack8(*reinterpret_cast<const uint4*>(xs + r * ld + cv * 8), f);
+    const long long stride = static_cast<long long>(gridDim.x) * nlanes;
+    for (long long r = static_cast<long long>(blockIdx.x) * nlanes + lane_r; r < rows_per_seg; r += 4 * stride) {
+      uint4 v[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      for (int u = 0; u < 4; ++u)
+        if (r + u * stride < rows_per_seg) v[u] = *reinterpret_cast<const uint4*>(xs + (r + u * stride) * ld + cv * 8);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (r + u * stride < rows_per_seg) {
+          float f[8];
+          unpack8(v[u], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        }
     }
   }
   for (int i = threadIdx.x; i < C8 * 8; i += blockDim.x) sh[i] = 0.f;
@@ -218,6 +226,49 @@ __global__ void pack_w_kernel(const float* __restrict__ w, bf16* __restrict__ ds
     }
     const float v = (co < Cout && ci < Cin) ? w[(static_cast<long long>(co) * Cin + ci) * ntaps + tap] : 0.f;
     dst[i] = __float2bfloat16(v);
+  }
+}
+
+// all weights of a model in ONE launch: block i packs elements [chunk0, chunk0 + kPackChunk) of tensor blocks[i].x
+struct PackDesc {
+  const float* src;
+  bf16* dst;
+  int Cout, Cin, ntaps, mode, Cout_p, Cin_p;
+};
+constexpr int kPackChunk = 4096;
+__global__ void pack_multi_kernel(const PackDesc* __restrict__ descs, const int2* __restrict__ blocks) {
+  const int2 blk = blocks[blockIdx.x];
+  const PackDesc d = descs[blk.x];
+  const long long n = static_cast<long long>(d.Cout_p) * d.Cin_p * d.ntaps;
+  const long long end = min(n, static_cast<long long>(blk.y) + kPackChunk);
+  for (long long i = blk.y + threadIdx.x; i < end; i += blockDim.x) {
+    int co, ci, tap;
+    if (d.mode == 0) {
+      ci = static_cast<int>(i % d.Cin_p);
+      tap = static_cast<int>((i / d.Cin_p) % d.ntaps);
+      co = static_cast<int>(i / (static_cast<long long>(d.Cin_p) * d.ntaps));
+    } else {
+      co = static_cast<int>(i % d.Cout_p);
+      tap = d.ntaps - 1 - static_cast<int>((i / d.Cout_p) % d.ntaps);
+      ci = static_cast<int>(i / (static_cast<long long>(d.Cout_p) * d.ntaps));
+    }
+    const float v = (co < d.Cout && ci < d.Cin) ? d.src[(static_cast<long long>(co) * d.Cin + ci) * d.ntaps + tap] : 0.f;
+    d.dst[i] = __float2bfloat16(v);
+  }
+}
+// out[c] = sum_m x[m, c] for a small fp32 matrix (fixed order); block = 32 columns x 8 row lanes
+__global__ void colsum_f32_kernel(const float* __restrict__ x, int M, int C, float* __restrict__ out) {
+  __shared__ float sh[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x, rl = threadIdx.y;
+  float a = 0.f;
+  if (c < C)
+    for (int m = rl; m < M; m += 8) a += x[static_cast<size_t>(m) * C + c];
+  sh[rl][threadIdx.x] = a;
+  __syncthreads();
+  if (rl == 0 && c < C) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) a += sh[k][threadIdx.x];
+    out[c] = a;
   }
 }
 
@@ -405,6 +456,16 @@ extern "C" int pddm_pack_conv_weight(const float* w, void* dst, int32_t Cout, in
     return PDDM_ERR_BAD_ARG;
   pack_w_kernel<<<grid_for(static_cast<long long>(Cout_pad) * Cin_pad * ntaps, 256), 256, 0, S(s)>>>(
       w, static_cast<bf16*>(dst), Cout, Cin, ntaps, mode, Cout_pad, Cin_pad);
+  return launch_status();
+}
+extern "C" int pddm_pack_weights_multi(const void* descs, const void* blocks, int32_t nblocks, pddm_stream_t s) {
+  if (!descs || !blocks || nblocks <= 0) return PDDM_ERR_BAD_ARG;
+  pack_multi_kernel<<<nblocks, 256, 0, S(s)>>>(static_cast<const PackDesc*>(descs), static_cast<const int2*>(blocks));
+  return launch_status();
+}
+extern "C" int pddm_colsum_f32(const float* x, int32_t M, int32_t C, float* out, pddm_stream_t s) {
+  if (!x || !out || M <= 0 || C <= 0) return PDDM_ERR_BAD_ARG;
+  colsum_f32_kernel<<<(C + 31) / 32, dim3(32, 8), 0, S(s)>>>(x, M, C, out);
   return launch_status();
 }
 extern "C" int pddm_im2col3x3(const float* x_nchw, void* out, int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t Kp,

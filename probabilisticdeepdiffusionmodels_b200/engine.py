@@ -502,11 +502,19 @@ class Engine(_Base):
         st = {"x": torch.zeros(batch_shape, dtype=torch.float32, device=dev), "opt": optimizer}
         params = [p for p in self.model.parameters() if p.requires_grad]
 
-        def body():
+        arena = ops.WeightArena()
+
+        def fwd_bwd():
             t = torch.randint(1, self.diffusion_steps + 1, (batch_shape[0],), device=dev)
             noise = torch.randn_like(st["x"])
             loss, per = self.loss_on(st["x"], t, noise)
             loss.backward()
+            return loss, per, t
+
+        def body():
+            arena.repack()  # one launch refreshes every bf16 weight pack from the fp32 masters
+            with arena.active():
+                loss, per, t = fwd_bwd()
             if grad_hook is not None:
                 grad_hook(params)
             optimizer.step()
@@ -517,14 +525,21 @@ class Engine(_Base):
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
+            with arena.recording():  # learn which packs the model asks for (forward and backward)
+                fwd_bwd()
+            arena.finalize(dev)
+            st["arena"] = arena
             for _ in range(3):
                 optimizer.zero_grad(set_to_none=True)
                 body()
         torch.cuda.current_stream(dev).wait_stream(side)
         graph = torch.cuda.CUDAGraph()
         optimizer.zero_grad(set_to_none=True)
+        from . import _lib
+        k0 = _lib.KERNELS[0]
         with torch.cuda.graph(graph):
             st["loss"], st["per"], st["t"] = body()
+        st["kernels_per_step"] = _lib.KERNELS[0] - k0  # kernels of this library captured in one step
         st["graph"] = graph
         self._train_graph = st
 

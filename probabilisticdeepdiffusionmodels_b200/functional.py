@@ -65,6 +65,9 @@ def _fill_taps(p, taps):
 
 
 # ------------------------------------------------------------------------------------------ conv / linear
+PACK_HOOK = [None]  # set by ops.WeightArena: (w, mode, cout_pad, cin_pad) -> packed tensor | None
+
+
 def pack_weight(w, mode, cout_pad=None, cin_pad=None):
     """fp32 [Cout, Cin, *k] -> bf16 GEMM operand (optionally zero-padded).
     mode 0: [Cout_pad, taps, Cin_pad]; mode 1 (dgrad): [Cin_pad, taps(flipped), Cout_pad]."""
@@ -73,6 +76,10 @@ def pack_weight(w, mode, cout_pad=None, cin_pad=None):
     cout, cin = w.shape[0], w.shape[1]
     ntaps = w.numel() // (cout * cin)
     cop, cip = cout_pad or cout, cin_pad or cin
+    if PACK_HOOK[0] is not None:
+        hit = PACK_HOOK[0](w, mode, cop, cip, ntaps)
+        if hit is not None:
+            return hit
     dst = torch.empty((cop, ntaps, cip) if mode == 0 else (cip, ntaps, cop), dtype=bf16, device=w.device)
     L.call("pddm_pack_conv_weight", L.ptr(w), L.ptr(dst), cout, cin, ntaps, mode, cop, cip, L.stream())
     return dst
@@ -96,9 +103,9 @@ def tap_gemm(x, wp, taps, B, H, W, *, bias=None, bcast=None, residual=None, out=
     p = L.ConvParams()
     p.x, p.w, p.y = L.ptr(x), L.ptr(wp), L.ptr(out)
     p.bias = L.ptr(_chk(bias, f32)) if bias is not None else None
-    if bcast is not None:
-        _chk(bcast, f32)
-        p.bcast, p.ld_bcast = L.ptr(bcast), bcast.shape[-1]
+    if bcast is not None:  # [B, Cout] fp32, rows may be strided (column slice of a wider matrix)
+        assert bcast.dtype == f32 and bcast.is_cuda and bcast.stride(-1) == 1 and bcast.shape[-1] == cout
+        p.bcast, p.ld_bcast = L.ptr(bcast), bcast.stride(0)
     if residual is not None:
         _chk(residual)
         assert residual.shape == out.shape
@@ -137,6 +144,14 @@ def colsum(x2d_bf16, C_):
     out = torch.empty(C_, dtype=f32, device=x2d_bf16.device)
     M = x2d_bf16.numel() // x2d_bf16.shape[-1]
     L.call("pddm_colsum", L.ptr(x2d_bf16), x2d_bf16.shape[-1], C.c_int64(M), C_, L.ptr(out), 0, L.stream())
+    return out
+
+
+def colsum_f32(x):
+    """fp32 [M, C] -> [C] (deterministic)."""
+    _chk(x, f32)
+    out = torch.empty(x.shape[-1], dtype=f32, device=x.device)
+    L.call("pddm_colsum_f32", L.ptr(x), x.numel() // x.shape[-1], x.shape[-1], L.ptr(out), L.stream())
     return out
 
 

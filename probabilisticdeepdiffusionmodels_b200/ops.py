@@ -51,6 +51,79 @@ def _packed(w, mode):
     return ent[1]
 
 
+class WeightArena:
+    """All bf16 weight packs of a model in one flat buffer, refreshed by ONE kernel launch per optimiser step.
+
+    Usage (Engine.capture_train_step): run one step inside ``recording()`` to learn which (weight, mode, padding)
+    packs the model asks for, ``finalize()``, then call ``repack()`` once per step and run the model inside
+    ``active()``: every ``pack_weight`` request is served as a view of the arena."""
+
+    def __init__(self):
+        self.requests = {}
+        self.views = {}
+        self.mode = "off"
+        self._descs = self._blocks = self._flat = None
+        self.nblocks = 0
+
+    @staticmethod
+    def _key(w, mode, cop, cip):
+        return (w.data_ptr(), mode, cop, cip)
+
+    def _hook(self, w, mode, cop, cip, ntaps):
+        key = self._key(w, mode, cop, cip)
+        if self.mode == "record":
+            self.requests[key] = (w, mode, cop, cip, ntaps)
+            return None
+        return self.views.get(key)
+
+    @contextlib.contextmanager
+    def recording(self):
+        prev, self.mode = (F.PACK_HOOK[0], self.mode), "record"
+        F.PACK_HOOK[0] = self._hook
+        try:
+            yield self
+        finally:
+            F.PACK_HOOK[0], self.mode = prev
+
+    @contextlib.contextmanager
+    def active(self):
+        prev, self.mode = (F.PACK_HOOK[0], self.mode), "serve"
+        F.PACK_HOOK[0] = self._hook
+        try:
+            yield self
+        finally:
+            F.PACK_HOOK[0], self.mode = prev
+
+    def finalize(self, device):
+        import ctypes as C
+
+        from . import _lib as L
+        total, metas = 0, []
+        for key, (w, mode, cop, cip, ntaps) in self.requests.items():
+            n = cop * cip * ntaps
+            metas.append((key, w, mode, cop, cip, ntaps, total, n))
+            total += (n + 7) // 8 * 8  # keep every pack 16-byte aligned
+        self._flat = torch.empty(max(total, 8), dtype=bf16, device=device)
+        descs = (L.PackDesc * len(metas))()
+        blocks = []
+        for i, (key, w, mode, cop, cip, ntaps, off, n) in enumerate(metas):
+            view = self._flat[off: off + n].view((cop, ntaps, cip) if mode == 0 else (cip, ntaps, cop))
+            self.views[key] = view
+            d = descs[i]
+            d.src, d.dst = w.data_ptr(), view.data_ptr()
+            d.Cout, d.Cin, d.ntaps, d.mode, d.Cout_pad, d.Cin_pad = w.shape[0], w.shape[1], ntaps, mode, cop, cip
+            blocks += [(i, c0) for c0 in range(0, n, L.PACK_CHUNK)]
+        self._descs = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).to(device)
+        self._blocks = torch.tensor(blocks, dtype=torch.int32).to(device)
+        self.nblocks = len(blocks)
+        self._keep = [m[1] for m in metas]
+        return self
+
+    def repack(self):
+        from . import _lib as L
+        L.call("pddm_pack_weights_multi", L.ptr(self._descs), L.ptr(self._blocks), self.nblocks, L.stream())
+
+
 def _empty(like):
     return torch.empty(0, dtype=f32, device=like.device)
 
@@ -163,7 +236,7 @@ def _conv_backward(ctx, dy, _daux):
     if st is not None and st[1] == dy._version:
         bias_sum = st[0]
     if per_sample is not None and bias_sum is None and need_db:
-        bias_sum = per_sample.sum(0)
+        bias_sum = F.colsum_f32(per_sample)
     want_db = need_db and bias_sum is None
     want_dbc = need_dbc and per_sample is None
     dx, dw, db, dbc = torch.ops.pddm.conv2d_bwd(dy, xin, weight, stride, upsample, in_h, in_w, need_dx, want_db, want_dbc)

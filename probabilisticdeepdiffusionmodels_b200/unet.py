@@ -31,6 +31,36 @@ def _conv(x, conv, bcast=None, residual=None, stride=1, upsample=False):
     return P.conv2d(x, conv.weight, conv.bias, bcast, residual, stride, upsample)[0]
 
 
+class _SplitCols(torch.autograd.Function):
+    """Column slices of one [B, sum(sizes)] matrix as separate tensors; the backward concatenates the slice
+    gradients with ONE kernel (torch slicing would zero-fill and add a full-size gradient per slice)."""
+
+    @staticmethod
+    def forward(ctx, x, sizes):
+        ctx.sizes = sizes
+        ctx.set_materialize_grads(False)
+        outs, off = [], 0
+        for n in sizes:
+            outs.append(x.narrow(1, off, n))
+            off += n
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        ref = next(g for g in grads if g is not None)
+        cols = [g if g is not None else ref.new_zeros((ref.shape[0], n)) for g, n in zip(grads, ctx.sizes)]
+        return torch.cat(cols, dim=1), None
+
+
+class EmbCtx:
+    """What a ResBlock needs from the timestep embedding: SiLU(emb) (bf16) and, when the model has already run all
+    ``emb_layers`` projections as ONE batched GEMM, this block's [B, Cout] slice of the result."""
+
+    def __init__(self, act, out=None):
+        self.act = act
+        self.out = out or {}
+
+
 class TimestepBlock(nn.Module):
     """Any module whose forward takes the (activated) timestep embedding as a second argument."""
 
@@ -120,7 +150,10 @@ class ResBlock(TimestepBlock):
 
     def _forward(self, x, emb):
         lin = self.emb_layers[1]
-        emb_out = P.linear(emb, lin.weight, lin.bias)  # fp32 [B, Cout] (or [B, 2*Cout])
+        emb_out = emb.out.get(id(self)) if isinstance(emb, EmbCtx) else None
+        if emb_out is None:
+            act = emb.act if isinstance(emb, EmbCtx) else emb
+            emb_out = P.linear(act, lin.weight, lin.bias)  # fp32 [B, Cout] (or [B, 2*Cout])
         h = _gn(x, self.in_layers[0], True)
         if self.use_scale_shift_norm:
             h = _conv(h, self.in_layers[2])
@@ -234,6 +267,18 @@ class UNetModel(nn.Module):
 
         self.out = nn.Sequential(normalization(ch), SiLU(),
                                  zero_module(conv_nd(dims, model_channels, out_channels, 3, padding=1)))
+        self.batch_emb_projections = True  # run the 1 + num_blocks emb_layers projections as one GEMM
+
+    def _emb_ctx(self, act):
+        """All ResBlock ``emb_layers`` share the input SiLU(emb) (unet.py:151-157): one [B, 4mc] x [sum Cout, 4mc]^T GEMM."""
+        if not self.batch_emb_projections or self.use_checkpoint:
+            return EmbCtx(act)
+        blocks = [m for m in self.modules() if isinstance(m, ResBlock)]
+        w_all = torch.cat([m.emb_layers[1].weight for m in blocks], dim=0)
+        b_all = torch.cat([m.emb_layers[1].bias for m in blocks], dim=0)
+        sizes = tuple(m.emb_layers[1].weight.shape[0] for m in blocks)
+        outs = _SplitCols.apply(P.linear(act, w_all, b_all), sizes)
+        return EmbCtx(act, {id(m): o for m, o in zip(blocks, outs)})
 
     @property
     def inner_dtype(self):
@@ -266,6 +311,7 @@ class UNetModel(nn.Module):
         out_dtype = x.dtype
         x = x.float().contiguous()
         _, emb = self.embed(timesteps.contiguous(), y)
+        emb = self._emb_ctx(emb)
 
         stem = self.input_blocks[0][0]
         if self.in_channels <= 4:
@@ -290,6 +336,7 @@ class UNetModel(nn.Module):
     def get_feature_vectors(self, x, timesteps, y=None):
         """src/modules/unet.py:497-527 (NCHW fp32 copies of the hidden states)."""
         _, emb = self.embed(timesteps.contiguous(), y)
+        emb = self._emb_ctx(emb)
         result = dict(down=[], up=[])
         x = x.float().contiguous()
         stem = self.input_blocks[0][0]
