@@ -3,15 +3,18 @@
 //   D[m, n] = sum_tap sum_c  X[pixel(m) + offset(tap), c] * Wp[n, tap, c]        (fp32 accumulate in TMEM)
 //
 // One persistent CTA per SM, warp-specialised:
-//   warp 0      TMA producer: per K-block one 4-D box load of the (shifted) NHWC activation tile -- out-of-bounds
-//               coordinates are zero-filled by the TMA unit, which is the conv's padding -- and one 2-D box load of the
-//               packed weight tile; both land in 128B/64B-swizzled K-major shared memory.
-//   warp 1      single-thread tcgen05.mma issuer (UMMA 128 x BLOCK_N x 16, bf16 -> fp32), accumulators double-buffered
-//               in tensor memory so the epilogue of tile i overlaps the main loop of tile i+1.
-//   warp 2      TMEM allocator.
+//   warps 1-3   TMA producers (K-blocks dealt round-robin): per K-block one 4-D box load of the (shifted) NHWC
+//               activation tile -- out-of-bounds coordinates are zero-filled by the TMA unit, which is the conv's
+//               padding -- and one 2-D box load of the packed weight tile; both land in 128B/64B-swizzled K-major
+//               shared memory.
+//   warp 0      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BLOCK_N x 16, bf16 -> fp32),
+//               accumulators double-buffered in tensor memory so the epilogue of tile i overlaps the main loop of
+//               tile i+1; two 128-row sub-tiles may share one weight tile.
 //   warps 4..7  epilogue: tcgen05.ld 32 lanes x 32 columns, + bias + per-sample broadcast (timestep embedding)
 //               + residual, convert, 128-bit stores.
 // Pipelines: smem full/empty mbarrier ring (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue).
+#include <stdlib.h>
+
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -29,11 +32,15 @@ struct ConvKArgs {
   int tap_db[PDDM_MAX_TAPS], tap_dh[PDDM_MAX_TAPS], tap_dw[PDDM_MAX_TAPS], tap_w[PDDM_MAX_TAPS];
   int out_H, out_W, out_sh, out_sw, out_oh, out_ow;
   int stages, a_slot_bytes, a_tx_bytes, b_bytes;
+  int mt;    // M sub-tiles (of 128 rows) per CTA tile sharing one B tile: 1 or 2
+  int nacc;  // accumulator stages in TMEM (2 = epilogue overlaps the next tile's main loop)
+  int dbg;   // PDDM_CONV_DBG experiment bits: 1 = empty epilogue, 2 = no A loads, 4 = no MMAs, 8 = no B loads
   uint32_t idesc, layout_type, sbo_bytes, tmem_cols;
 };
 
 constexpr int kConvThreads = 256;
 constexpr int kMaxStages = 8;
+constexpr int kNumProducers = 3;
 constexpr int kMaxAddRows = 8;                   // tile rows may span up to this many samples with a staged bias/bcast
 constexpr int kAddBytes = kMaxAddRows * 256 * 4;  // smem for the staged bias + per-sample broadcast vector
 
@@ -42,7 +49,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const __grid_constant__ ConvKArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int stage_bytes = a.a_slot_bytes + a.b_bytes;
+  const int stage_bytes = a.mt * a.a_slot_bytes + a.b_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.stages * stage_bytes);
   uint64_t* full_bar = bars;                      // [stages]
   uint64_t* empty_bar = bars + kMaxStages;        // [stages]
@@ -53,14 +60,15 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = a.m_tiles * a.n_tiles;
+  const int m_super = (a.m_tiles + a.mt - 1) / a.mt;  // CTA tiles along M (mt sub-tiles each)
+  const int total_tiles = m_super * a.n_tiles;
   const int total_kb = a.ntaps * a.kblocks_per_tap;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 1 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == 0 && lane == 0) {
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -71,41 +79,57 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_ptr, a.tmem_cols);
+  if (warp == 0) tmem_alloc(tmem_ptr, a.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+  if (warp >= 1 && warp <= 3) {
+    // ---------------------------------------------------------------- TMA producers (3 single-lane issuers)
+    // Issuing one K-block (barrier wait + expect_tx + a 4-D and a 2-D bulk-tensor copy) costs ~700 cycles of
+    // issue latency on one thread, more than the 256-512 cycles of tensor work it feeds; K-blocks are therefore
+    // dealt round-robin to three producer warps.  Stage and parity follow from the global K-block index.
+    // (the loops run warp-uniformly and only the issue is predicated on one elected lane: inside a divergent
+    //  `if (lane == 0)` region the compiler has to wrap every UTMALDG / UTCHMMA / SYNCS operand in a
+    //  uniform-register waterfall loop, which costs ~100-200 cycles per instruction)
+    {
+      const int pid = warp - 1;
+      int g = 0;  // global K-block index of this CTA
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_tile = tile % a.m_tiles, n_tile = tile / a.m_tiles;
-        const int tw = m_tile % a.tiles_w;
-        const int th = (m_tile / a.tiles_w) % a.tiles_h;
-        const int tb = m_tile / (a.tiles_w * a.tiles_h);
-        const int b0 = tb * a.BB, h0 = th * a.BH, w0 = tw * a.BW;
+        const int ms = tile % m_super, n_tile = tile / m_super;
+        int b0[2], h0[2], w0[2];
+        for (int hf = 0; hf < a.mt; ++hf) {
+          const int m_tile = ms * a.mt + hf;  // may run past m_tiles: coordinates then fall outside -> zero fill
+          b0[hf] = (m_tile / (a.tiles_w * a.tiles_h)) * a.BB;
+          h0[hf] = ((m_tile / a.tiles_w) % a.tiles_h) * a.BH;
+          w0[hf] = (m_tile % a.tiles_w) * a.BW;
+        }
         for (int tap = 0; tap < a.ntaps; ++tap) {
-          const int cb = b0 + a.tap_db[tap], ch = h0 + a.tap_dh[tap], cw = w0 + a.tap_dw[tap];
-          for (int kc = 0; kc < a.kblocks_per_tap; ++kc) {
+          for (int kc = 0; kc < a.kblocks_per_tap; ++kc, ++g) {
+            if (g % kNumProducers != pid) continue;
+            const int stage = g % a.stages;
+            const uint32_t phase = (g / a.stages) & 1;
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_expect_tx(&full_bar[stage], a.a_tx_bytes + a.b_bytes);
-            uint8_t* sa = smem + stage * stage_bytes;
-            tma_load_4d(sa, &tmA, &full_bar[stage], kc * a.bk, cw, ch, cb);
-            tma_load_2d(sa + a.a_slot_bytes, &tmB, &full_bar[stage], (a.tap_w[tap] * a.kblocks_per_tap + kc) * a.bk,
-                        n_tile * a.block_n);
-            if (++stage == a.stages) {
-              stage = 0;
-              phase ^= 1;
+            if (elect_one()) {
+              mbar_expect_tx(&full_bar[stage],
+                             ((a.dbg & 2) ? 0 : a.mt * a.a_tx_bytes) + ((a.dbg & 8) ? 0 : a.b_bytes));
+              uint8_t* sa = smem + stage * stage_bytes;
+              for (int hf = 0; hf < a.mt && !(a.dbg & 2); ++hf)
+                tma_load_4d(sa + hf * a.a_slot_bytes, &tmA, &full_bar[stage], kc * a.bk, w0[hf] + a.tap_dw[tap],
+                            h0[hf] + a.tap_dh[tap], b0[hf] + a.tap_db[tap]);
+              if (!(a.dbg & 8))
+                tma_load_2d(sa + a.mt * a.a_slot_bytes, &tmB, &full_bar[stage],
+                            (a.tap_w[tap] * a.kblocks_per_tap + kc) * a.bk, n_tile * a.block_n);
             }
+            __syncwarp();
           }
         }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
+  } else if (warp == 0) {
+    // ---------------------------------------------------------------- MMA issuer (warp-uniform loop, one lane issues)
+    {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -113,28 +137,36 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * a.block_n;
+        const uint32_t d_tmem = tmem_base + acc * a.mt * a.block_n;
         for (int kb = 0; kb < total_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-          const uint32_t sb = sa + a.a_slot_bytes;
-          const uint64_t adesc = make_smem_desc(sa, 16, a.sbo_bytes, a.layout_type);
-          const uint64_t bdesc = make_smem_desc(sb, 16, a.sbo_bytes, a.layout_type);
-          const int ksteps = a.bk >> 4;
-          for (int k = 0; k < ksteps; ++k) {
-            // advance 16 elements (32 B) along K inside the swizzled row: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, a.idesc, (kb | k) != 0);
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+            const uint32_t sb = sa + a.mt * a.a_slot_bytes;
+            const uint64_t bdesc = make_smem_desc(sb, 16, a.sbo_bytes, a.layout_type);
+            const int ksteps = a.bk >> 4;
+            for (int hf = 0; hf < a.mt && !(a.dbg & 4); ++hf) {  // the sub-tiles reuse the B tile already in smem
+              const uint64_t adesc = make_smem_desc(sa + hf * a.a_slot_bytes, 16, a.sbo_bytes, a.layout_type);
+              for (int k = 0; k < ksteps; ++k) {
+                // advance 16 elements (32 B) along K inside the swizzled row: +2 in the (addr >> 4) field
+                umma_bf16(d_tmem + hf * a.block_n, adesc + 2 * k, bdesc + 2 * k, a.idesc, (kb | k) != 0);
+              }
+            }
+            umma_commit(&empty_bar[stage]);
           }
-          umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == a.stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        if (elect_one()) umma_commit(&tmem_full[acc]);
+        __syncwarp();
+        if (++acc == a.nacc) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
       }
     }
   } else if (warp >= 4) {
@@ -149,7 +181,9 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const bool has_add = (a.bias != nullptr) || (a.bcast != nullptr);
     const bool stage_add = has_add && a.BB <= kMaxAddRows;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_tile = tile % a.m_tiles, n_tile = tile / a.m_tiles;
+     const int ms = tile % m_super, n_tile = tile / m_super;
+     for (int hf = 0; hf < a.mt; ++hf) {
+      const int m_tile = ms * a.mt + hf;
       const int tw = m_tile % a.tiles_w;
       const int th = (m_tile / a.tiles_w) % a.tiles_h;
       const int tb = m_tile / (a.tiles_w * a.tiles_h);
@@ -189,9 +223,9 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int g = 0; g < 4; ++g)
           if (nbase + g * 8 < a.Cout) rres[0][g] = __ldg(reinterpret_cast<const uint4*>(res_b + nbase + g * 8));
       }
-      mbar_wait(&tmem_full[acc], acc_phase);
+      if (hf == 0) mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * a.block_n;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (acc * a.mt + hf) * a.block_n;
       uint32_t r[2][32];
       tmem_ld32(taddr, r[0]);
 #pragma unroll
@@ -208,7 +242,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
           const int n0 = nbase + c * 32;
-          if (valid && n0 < a.Cout) {
+          if (valid && n0 < a.Cout && !(a.dbg & 1)) {
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[c & 1][j]);
@@ -266,18 +300,21 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
       }
+     }  // sub-tiles
       // all of this warp's TMEM reads have completed (last tmem_ld_wait): hand the accumulator back
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (++acc == a.nacc) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, a.tmem_cols);
   }
@@ -357,10 +394,16 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
   a.a_tx_bytes = a.BW * a.BH * a.BB * swz;
   a.b_bytes = a.block_n * swz;
   a.idesc = make_idesc_bf16(128, a.block_n, 0, 0);
+  // Two 128-row sub-tiles per CTA tile share each B (weight) tile: the kernel is bound by the L2 -> shared-memory
+  // fill rate (~42 B/clk/SM), and this cuts the bytes per MMA by 25-33%.  Used when it still leaves >= 1 full wave.
+  a.mt = 1;  // measured: sharing B across two sub-tiles does not pay (the kernel is issue-latency, not L2, bound)
+  if (getenv("PDDM_CONV_MT")) a.mt = atoi(getenv("PDDM_CONV_MT")) == 2 ? 2 : 1;
+  a.nacc = (2 * a.mt * a.block_n <= 512) ? 2 : 1;
+  a.dbg = getenv("PDDM_CONV_DBG") ? atoi(getenv("PDDM_CONV_DBG")) : 0;
   uint32_t cols = 32;
-  while (cols < static_cast<uint32_t>(2 * a.block_n)) cols <<= 1;
+  while (cols < static_cast<uint32_t>(a.nacc * a.mt * a.block_n)) cols <<= 1;
   a.tmem_cols = cols;
-  const int stage_bytes = a.a_slot_bytes + a.b_bytes;
+  const int stage_bytes = a.mt * a.a_slot_bytes + a.b_bytes;
   const int budget = device_info().max_smem_optin - 1024 - 512 - kAddBytes;
   int stages = budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -394,7 +437,7 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
       return PDDM_ERR_CUDA;
     attr_set = true;
   }
-  const int total_tiles = a.m_tiles * a.n_tiles;
+  const int total_tiles = ((a.m_tiles + a.mt - 1) / a.mt) * a.n_tiles;
   const int grid = total_tiles < device_info().sm_count ? total_tiles : device_info().sm_count;
   conv_fwd_kernel<<<grid, kConvThreads, smem_bytes, stream>>>(tmA, tmB, a);
   return launch_status();

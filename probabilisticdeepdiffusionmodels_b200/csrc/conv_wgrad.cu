@@ -52,11 +52,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     for (int i = threadIdx.x; i < n16; i += kWgThreads) z[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
   }
-  if (warp == 0 && lane == 0) {
+  if (warp == 1 && lane == 0) {
     tma_prefetch_desc(&tmDY);
     tma_prefetch_desc(&tmX);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == 0 && lane == 0) {
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -67,7 +67,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_ptr, a.tmem_cols);
+  if (warp == 0) tmem_alloc(tmem_ptr, a.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -83,37 +83,43 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     split = item / a.m_tiles;
   };
 
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+  if (warp >= 1 && warp <= 3) {
+    // TMA producers: a K-block needs 2 + n_chunks bulk-tensor copies (~200 cycles of issue latency each on one
+    // thread), far more than the 512 cycles of tensor work it feeds, so K-blocks are dealt round-robin to three
+    // single-lane producers; stage and parity follow from the global K-block index.
+    // (warp-uniform loop, issue predicated on one elected lane: see conv_fwd.cu)
+    {
+      const int pid = warp - 1;
+      int g = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         int tap, m_tile, n_tile, split;
         decode(item, tap, m_tile, n_tile, split);
         const int kb0 = split * a.kb_per_split;
         const int kb1 = min(kb0 + a.kb_per_split, a.k_blocks);
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb, ++g) {
+          if (g % 3 != pid) continue;
+          const int stage = g % a.stages;
+          const uint32_t phase = (g / a.stages) & 1;
           const int tw = kb % a.tiles_w;
           const int th = (kb / a.tiles_w) % a.tiles_h;
           const int tb = kb / (a.tiles_w * a.tiles_h);
           const int b0 = tb * a.BB, h0 = th * a.BH, w0 = tw * a.BW;
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], a.tx_bytes);
-          uint8_t* sa = smem + stage * stage_bytes;
-          tma_load_4d(sa, &tmDY, &full_bar[stage], m_tile * 128, w0, h0, b0);
-          tma_load_4d(sa + kChunkBytes, &tmDY, &full_bar[stage], m_tile * 128 + 64, w0, h0, b0);
-          for (int c = 0; c < a.n_chunks; ++c)
-            tma_load_4d(sa + a_bytes + c * kChunkBytes, &tmX, &full_bar[stage], n_tile * a.block_n + c * 64,
-                        w0 + a.tap_dw[tap], h0 + a.tap_dh[tap], b0 + a.tap_db[tap]);
-          if (++stage == a.stages) {
-            stage = 0;
-            phase ^= 1;
+          if (elect_one()) {
+            mbar_expect_tx(&full_bar[stage], a.tx_bytes);
+            uint8_t* sa = smem + stage * stage_bytes;
+            tma_load_4d(sa, &tmDY, &full_bar[stage], m_tile * 128, w0, h0, b0);
+            tma_load_4d(sa + kChunkBytes, &tmDY, &full_bar[stage], m_tile * 128 + 64, w0, h0, b0);
+            for (int c = 0; c < a.n_chunks; ++c)
+              tma_load_4d(sa + a_bytes + c * kChunkBytes, &tmX, &full_bar[stage], n_tile * a.block_n + c * 64,
+                          w0 + a.tap_dw[tap], h0 + a.tap_dh[tap], b0 + a.tap_db[tap]);
           }
+          __syncwarp();
         }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
+  } else if (warp == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -129,23 +135,27 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-          const uint32_t sb = sa + a_bytes;
-          // MN-major SW128: LBO = distance between 64-channel chunks, SBO = 8 pixel rows * 128 B
-          const uint64_t adesc = make_smem_desc(sa, kChunkBytes, 1024, kLayoutSW128);
-          const uint64_t bdesc = make_smem_desc(sb, kChunkBytes, 1024, kLayoutSW128);
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+            const uint32_t sb = sa + a_bytes;
+            // MN-major SW128: LBO = distance between 64-channel chunks, SBO = 8 pixel rows * 128 B
+            const uint64_t adesc = make_smem_desc(sa, kChunkBytes, 1024, kLayoutSW128);
+            const uint64_t bdesc = make_smem_desc(sb, kChunkBytes, 1024, kLayoutSW128);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // 16 pixel rows per MMA = 2048 B = 128 in the (addr >> 4) field
-            umma_bf16(d_tmem, adesc + 128 * k, bdesc + 128 * k, a.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              // 16 pixel rows per MMA = 2048 B = 128 in the (addr >> 4) field
+              umma_bf16(d_tmem, adesc + 128 * k, bdesc + 128 * k, a.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);
           }
-          umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == a.stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);
+        if (elect_one()) umma_commit(&tmem_full[acc]);
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -191,7 +201,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, a.tmem_cols);
   }

@@ -1,0 +1,72 @@
+"""Data-parallel host logic over gloo, world_size 2, on CPU: batch sharding and the flat-bucket gradient
+all-reduce (the N>1 path of bench.py uses the same code over NCCL)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from probabilisticdeepdiffusionmodels_b200 import parallel
+    r, w, _ = parallel.init_from_env("gloo")
+    assert (r, w) == (rank, world)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+    if rank == 1:  # ranks start different: the broadcast must fix that
+        with torch.no_grad():
+            for p in net.parameters():
+                p.add_(1.0)
+    parallel.broadcast_parameters(net)
+    x = torch.arange(7 * 6, dtype=torch.float32).reshape(7, 6) / 10.0
+    y = torch.arange(7 * 3, dtype=torch.float32).reshape(7, 3) / 5.0
+    xs, ys = parallel.shard_batch(x, rank, world), parallel.shard_batch(y, rank, world)
+    assert xs.shape[0] == (4 if rank == 0 else 3)
+    # per-rank loss scaled so that AVERAGING the rank gradients reproduces the global-batch mean loss
+    loss = ((net(xs) - ys) ** 2).sum() / x.shape[0] * world
+    loss.backward()
+    params = list(net.parameters())
+    parallel.FlatGradAllReduce()(params)
+    if rank == 0:
+        ref = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+        ref.load_state_dict(net.state_dict())
+        (((ref(x) - y) ** 2).sum() / x.shape[0]).backward()
+        errs = [float((a.grad - b.grad).abs().max()) for a, b in zip(params, ref.parameters())]
+        torch.save({"errs": errs}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_grad_allreduce_equals_single_process_gradient(tmp_path):
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    errs = torch.load(out)["errs"]
+    assert max(errs) < 1e-5, errs
+
+
+def test_shard_batch_covers_everything():
+    from probabilisticdeepdiffusionmodels_b200.parallel import shard_batch
+    x = torch.arange(10)
+    for world in (1, 2, 3, 4, 8):
+        parts = [shard_batch(x, r, world) for r in range(world)]
+        assert torch.equal(torch.cat(parts), x)
+        assert max(p.numel() for p in parts) - min(p.numel() for p in parts) <= 1
+
+
+def test_single_process_is_a_noop():
+    from probabilisticdeepdiffusionmodels_b200.parallel import FlatGradAllReduce
+    p = torch.nn.Parameter(torch.ones(3))
+    p.grad = torch.full((3,), 2.0)
+    FlatGradAllReduce()([p])
+    assert p.grad.tolist() == [2.0, 2.0, 2.0]
