@@ -86,6 +86,55 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# forward 3x3 conv census of config/model/unet.yaml at 32x32: (H, Cin, Cout, count)
+CONV_CENSUS = [(32, 128, 128, 10), (16, 256, 256, 10), (16, 512, 256, 3), (32, 256, 128, 3), (32, 256, 256, 1),
+               (32, 384, 128, 1), (8, 256, 256, 11), (8, 512, 256, 4), (16, 384, 256, 1), (4, 256, 256, 14),
+               (4, 512, 256, 4)]
+
+
+def dominant_kernel_roofline(dev, B, burst_tflops, src):
+    """Time the dominant kernel (conv_fwd_kernel: the tcgen05 tap-GEMM behind every conv forward and data gradient)
+    live with CUDA events on the model's own 3x3 conv census: one launch per layer, distinct input/weight tensors per
+    layer (0.6 GB of operands, > L2).  achieved = algorithmic FLOPs of the census / time of the census."""
+    import torch
+
+    from probabilisticdeepdiffusionmodels_b200 import _lib, ops
+    P = torch.ops.pddm
+    g = torch.Generator(device=dev).manual_seed(0)
+    layers, flops = [], 0.0
+    for H, cin, cout, count in CONV_CENSUS:
+        for _ in range(count):
+            x = torch.randn((B, H, H, cin), generator=g, device=dev).to(torch.bfloat16)
+            w = torch.randn((cout, cin, 3, 3), generator=g, device=dev) * 0.02
+            b = torch.zeros(cout, device=dev)
+            layers.append((x, w, b))
+            flops += 2.0 * B * H * H * cout * cin * 9
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.no_grad(), ops.frozen_weights():
+        for _ in range(3):  # warm-up (weight packs cached)
+            for x, w, b in layers:
+                P.conv2d(x, w, b, None, None, 1, False)
+        torch.cuda.synchronize(dev)
+        k0 = _lib.KERNELS[0]
+        reps = 5
+        e0.record()
+        for _ in range(reps):
+            for x, w, b in layers:
+                P.conv2d(x, w, b, None, None, 1, False)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        launches = (_lib.KERNELS[0] - k0) // reps
+    sec = e0.elapsed_time(e1) * 1e-3 / reps
+    ach = flops / sec / 1e12
+    return {"bound": "tensor", "achieved": ach, "peak": burst_tflops, "unit": "TFLOP/s", "frac": ach / burst_tflops,
+            # dram__bytes_read+write of one 32x32 128->128 launch from the ncu --set full capture in profiles/
+            "traffic": 34.04e6, "traffic_note": "per launch of the 3x3 32x32 128->128 B=128 layer (algorithmic: 67 MB; "
+                                                "the output stays in L2 during the capture)",
+            "kernel": "pddm::conv_fwd_kernel", "launches_timed": int(launches), "us_per_launch": sec / launches * 1e6,
+            "flops_per_census": flops, "peak_source": f"{src} (burst bf16, kernel timed alone)",
+            "workload": "forward 3x3 conv census of the CIFAR UNet at B=128 (62 launches), CUDA events"}
+
+
 def cpu_reference_arm(steps, warmup, batch=CPU_BATCH, threads=None):
     """The reference's own PyTorch path (CPU oracle port, fp32): training step with Adam + a few reverse steps."""
     import numpy as np
@@ -262,9 +311,10 @@ def main():
     fwd = fwd_flops_per_image(arch, RES)
     train_flops = 3 * fwd
     achieved = img_s / world * train_flops / 1e12  # per GPU
-    roof = {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
-            "traffic": None, "peak_source": f"{src} (sustained bf16; burst {burst})",
-            "scope": "whole train step per GPU (algorithmic 3 x fwd FLOPs/img x img/s); per-kernel numbers in profiles/"}
+    roof_step = {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
+                 "frac": achieved / sustained, "peak_source": f"{src} (sustained bf16; burst {burst})",
+                 "scope": "whole train step per GPU (algorithmic 3 x fwd FLOPs/img x img/s)"}
+    roof = dominant_kernel_roofline(dev, B, burst, src)
     if sampling is not None:
         s_ach = sampling["image_steps_per_s"] / world * fwd / 1e12
         sampling["roofline_frac"] = s_ach / sustained
@@ -275,7 +325,7 @@ def main():
             "e2e": {"value": img_s_e2e, "unit": "img/s", "h2d_bytes_per_step": host_x.numel() * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e, "last_loss": loss_val},
             "gpu_launches": int(kernels_per_step * args.steps), "kernels_per_step": int(kernels_per_step),
-            "roofline": roof, "sampling": sampling}
+            "roofline": roof, "roofline_step": roof_step, "sampling": sampling}
     if not args.no_cpu_baseline and world == 1:
         r = cpu_reference_arm(2, 1)
         line["cpu_baseline"] = {"value": r["train_img_s"], "unit": "img/s", "cores": r["cores"], "kind": "port",
