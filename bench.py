@@ -331,6 +331,8 @@ def main():
         line["cpu_baseline"] = {"value": r["train_img_s"], "unit": "img/s", "cores": r["cores"], "kind": "port",
                                 "sample": r["sample"], "samples_per_s": r["samples_s"]}
     print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

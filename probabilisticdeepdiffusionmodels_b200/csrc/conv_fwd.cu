@@ -228,24 +228,26 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (acc * a.mt + hf) * a.block_n;
       uint32_t r[2][32];
       tmem_ld32(taddr, r[0]);
+      for (int cp = 0; cp < nchunks; cp += 2) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+       for (int ci = 0; ci < 2; ++ci) {
+        const int c = cp + ci;
         if (c < nchunks) {
           tmem_ld_wait();
           if (c + 1 < nchunks) {
-            tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);  // overlaps with the math/stores of chunk c
+            tmem_ld32(taddr + (c + 1) * 32, r[(ci + 1) & 1]);  // overlaps with the math/stores of chunk c
             if (res_bf16 && valid) {
 #pragma unroll
               for (int g = 0; g < 4; ++g)
                 if (nbase + (c + 1) * 32 + g * 8 < a.Cout)
-                  rres[(c + 1) & 1][g] = __ldg(reinterpret_cast<const uint4*>(res_b + nbase + (c + 1) * 32 + g * 8));
+                  rres[(ci + 1) & 1][g] = __ldg(reinterpret_cast<const uint4*>(res_b + nbase + (c + 1) * 32 + g * 8));
             }
           }
           const int n0 = nbase + c * 32;
           if (valid && n0 < a.Cout && !(a.dbg & 1)) {
             float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[c & 1][j]);
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[ci][j]);
             if (stage_add) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
@@ -266,7 +268,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
                 if (a.residual) {
                   if (res_bf16) {
-                    const uint4 rv = rres[c & 1][g];
+                    const uint4 rv = rres[ci][g];
                     const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -299,6 +301,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
         }
+       }
       }
      }  // sub-tiles
       // all of this warp's TMEM reads have completed (last tmem_ld_wait): hand the accumulator back
@@ -407,6 +410,7 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
   const int budget = device_info().max_smem_optin - 1024 - 512 - kAddBytes;
   int stages = budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
+  if (getenv("PDDM_CONV_STAGES") && atoi(getenv("PDDM_CONV_STAGES")) < stages) stages = atoi(getenv("PDDM_CONV_STAGES"));
   if (stages < 2) return PDDM_ERR_UNSUPPORTED;
   a.stages = stages;
   const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 + 512 + kAddBytes;
