@@ -30,6 +30,7 @@ struct AttnArgs {
   float scale_log2e, scale;
   uint32_t tmem_cols;
   uint32_t off_q, off_do, off_k, off_v, off_p, off_bar;  // smem offsets
+  int pass;  // backward only: 0 = dQ, dK, dV in one launch; 1 = dQ + dV; 2 = dK (two launches when TMEM is short)
 };
 
 // ---- descriptor helpers -------------------------------------------------------------------------
@@ -215,7 +216,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int h = blockIdx.x % a.heads, b = blockIdx.x / a.heads;
   const int ns = (a.Tp + 127) / 128;  // key tiles of 128
   const int r0w = a.Tp > a.d ? a.Tp : a.d;
-  const int col_dv = r0w, col_dk = r0w + ns * a.d;
+  const bool do_v = a.pass != 2, do_k = a.pass != 1;  // dQ is produced together with dV
+  const int col_dv = r0w, col_dk = (a.pass == 0) ? r0w + ns * a.d : r0w;
 
   if (tid == 0) {
     mbar_init(bar_kv, 1);
@@ -300,7 +302,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int kk = 0; kk < a.d / 16; ++kk)  // dP = dO V^T
         umma_bf16(tmem, desc_kmajor(sDO, 128, a.cw, kk), desc_kmajor(sV, a.Tp, a.cw, kk), idesc_s, kk > 0);
       const uint32_t idesc_t = make_idesc_bf16(128, a.d, 1, 1);
-      for (int j = 0; j < ns; ++j)  // dV_j += P_j^T dO
+      for (int j = 0; j < ns && do_v; ++j)  // dV_j += P_j^T dO
         for (int kk = 0; kk < 8; ++kk)
           umma_bf16(tmem + col_dv + j * a.d, desc_p_mnmajor(sP, kk, j), desc_mnmajor(sDO, 128, a.cw, kk, 0), idesc_t,
                     (qt > 0 || kk > 0) ? 1u : 0u);
@@ -326,10 +328,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_after();
     if (tid == 0) {
       const uint32_t idesc_q = make_idesc_bf16(128, a.d, 0, 1);
-      for (int kk = 0; kk < a.Tp / 16; ++kk)  // dQ = dS K
+      for (int kk = 0; kk < a.Tp / 16 && do_v; ++kk)  // dQ = dS K
         umma_bf16(tmem, desc_p_kmajor(sP, kk), desc_mnmajor(sK, a.Tp, a.cw, kk, 0), idesc_q, kk > 0);
       const uint32_t idesc_t = make_idesc_bf16(128, a.d, 1, 1);
-      for (int j = 0; j < ns; ++j)  // dK_j += dS_j^T Q
+      for (int j = 0; j < ns && do_k; ++j)  // dK_j += dS_j^T Q
         for (int kk = 0; kk < 8; ++kk)
           umma_bf16(tmem + col_dk + j * a.d, desc_p_mnmajor(sP, kk, j), desc_mnmajor(sQ, 128, a.cw, kk, 0), idesc_t,
                     (qt > 0 || kk > 0) ? 1u : 0u);
@@ -339,7 +341,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mma_phase ^= 1;
     tc_fence_after();
     bf16* dq = a.y + (static_cast<size_t>(b) * a.T + (valid ? t : 0)) * (3 * a.C) + cq;
-    store_row_from_tmem(trow, 0, a.d, 1.f, dq, valid);
+    if (do_v) store_row_from_tmem(trow, 0, a.d, 1.f, dq, valid);
     tc_fence_before();
     __syncthreads();  // R0 and the Q/dO tiles are free for the next query tile
     tc_fence_after();
@@ -348,8 +350,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int s = j * 128 + tid;
     const bool valid = s < a.T;
     bf16* base = a.y + (static_cast<size_t>(b) * a.T + (valid ? s : 0)) * (3 * a.C) + cq;
-    store_row_from_tmem(trow, col_dk + j * a.d, a.d, 1.f, base + a.d, valid);
-    store_row_from_tmem(trow, col_dv + j * a.d, a.d, 1.f, base + 2 * a.d, valid);
+    if (do_k) store_row_from_tmem(trow, col_dk + j * a.d, a.d, 1.f, base + a.d, valid);
+    if (do_v) store_row_from_tmem(trow, col_dv + j * a.d, a.d, 1.f, base + 2 * a.d, valid);
   }
   tc_fence_before();
   __syncthreads();
@@ -431,8 +433,10 @@ extern "C" int pddm_attn_bwd(const pddm_attn_bwd_params* p, pddm_stream_t s_) {
   a.y = static_cast<bf16*>(p->dqkv);
   a.lse = const_cast<float*>(p->lse);
   const int ns = (a.Tp + 127) / 128;
-  const uint32_t need = (a.Tp > a.d ? a.Tp : a.d) + 2 * ns * a.d;
-  if (need > 512) return PDDM_ERR_UNSUPPORTED;  // TODO(round 2): channel-split pass for d=96,T=256
+  uint32_t need = (a.Tp > a.d ? a.Tp : a.d) + 2 * ns * a.d;
+  const bool two_pass = need > 512;  // e.g. d = 96, T = 256: dV and dK accumulators do not fit together
+  if (two_pass) need = (a.Tp > a.d ? a.Tp : a.d) + ns * a.d;
+  if (need > 512) return PDDM_ERR_UNSUPPORTED;
   uint32_t cols = 32;
   while (cols < need) cols <<= 1;
   a.tmem_cols = cols;
@@ -455,6 +459,15 @@ extern "C" int pddm_attn_bwd(const pddm_attn_bwd_params* p, pddm_stream_t s_) {
   if (cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            device_info().max_smem_optin) != cudaSuccess)
     return PDDM_ERR_CUDA;
-  attn_bwd_kernel<<<a.B * a.heads, 128, smem, s>>>(tmQ, tmKV, tmDO, a);
+  if (!two_pass) {
+    a.pass = 0;
+    attn_bwd_kernel<<<a.B * a.heads, 128, smem, s>>>(tmQ, tmKV, tmDO, a);
+  } else {
+    a.pass = 1;
+    attn_bwd_kernel<<<a.B * a.heads, 128, smem, s>>>(tmQ, tmKV, tmDO, a);
+    if (cudaPeekAtLastError() != cudaSuccess) return PDDM_ERR_CUDA;
+    a.pass = 2;
+    attn_bwd_kernel<<<a.B * a.heads, 128, smem, s>>>(tmQ, tmKV, tmDO, a);
+  }
   return launch_status();
 }

@@ -444,7 +444,13 @@ static int colsum_launch(const void* x, int ld, long long rows_per_seg, int segs
 extern "C" int pddm_colsum(const void* x, int32_t ld, int64_t M, int32_t C, float* out, int32_t accumulate,
                            pddm_stream_t s) {
   if (!x || !out || M <= 0 || C <= 0) return PDDM_ERR_BAD_ARG;
-  return colsum_launch(x, ld, M, 1, C, out, C, accumulate, S(s));
+  // wide matrices (e.g. the batched timestep-embedding projection) are reduced in column panels
+  for (int c0 = 0; c0 < C; c0 += 4096) {
+    const int cw = C - c0 < 4096 ? C - c0 : 4096;
+    int rc = colsum_launch(static_cast<const bf16*>(x) + c0, ld, M, 1, cw, out + c0, cw, accumulate, S(s));
+    if (rc) return rc;
+  }
+  return PDDM_OK;
 }
 extern "C" int pddm_colsum_per_sample(const void* x, int32_t B, int32_t HW, int32_t C, float* out, pddm_stream_t s) {
   if (!x || !out || B <= 0 || HW <= 0 || C <= 0) return PDDM_ERR_BAD_ARG;

@@ -108,3 +108,22 @@ def test_cpu_input_raises():
     m = get_model(28, dict(MODEL_CONFIGS["unet_small_grey"]))
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 1, 28, 28), torch.ones(1))
+
+
+def test_unet_celeba64_config_trains():
+    """BASELINE config 5 shape: unet_celeba.yaml at 64x64 (attention d=96 at T=256 -> two-pass backward, d=128 at T=64)."""
+    cfg = MODEL_CONFIGS["unet_celeba"]
+    m, arch, P = build(cfg, 64, 3)
+    _, t, noise = synth_batch(11, 2, 3, 64, 1000)
+    Pr = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    yr = unet_forward(Pr, arch, noise, t)
+    gy = torch.from_numpy(np.random.RandomState(8).standard_normal(tuple(yr.shape)).astype(np.float32))
+    (yr * gy).sum().backward()
+    y = m(noise.cuda(), t.cuda())
+    (y * gy.cuda()).sum().backward()
+    assert rel(y, yr.detach()) < 2e-2
+    got = dict(m.named_parameters())
+    assert "input_blocks.9.1.qkv.weight" in got and "input_blocks.13.1.qkv.weight" in got  # d=96/T=256, d=128/T=64
+    errs = {n: rel(got[n].grad, Pr[n].grad) for n in Pr if float(Pr[n].grad.norm()) > 1e-3}
+    bad = {n: round(v, 3) for n, v in errs.items() if v > 0.1}
+    assert not bad, bad

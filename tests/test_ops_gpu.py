@@ -134,7 +134,7 @@ def test_gn_silu_fwd_bwd(P, B, H, W, C, silu, ss, xdtype):
 
 
 ATTN_CASES = [(2, 256, 4, 64), (3, 64, 4, 64), (2, 16, 4, 64), (2, 49, 1, 64), (2, 64, 2, 32), (1, 64, 4, 128),
-              (2, 256, 1, 32), (2, 200, 2, 64)]
+              (2, 256, 1, 32), (2, 200, 2, 64), (2, 256, 4, 96), (2, 64, 4, 128)]
 
 
 @pytest.mark.parametrize("B,T,heads,d", ATTN_CASES)
