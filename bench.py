@@ -195,6 +195,7 @@ def main():
     ap.add_argument("--sample-steps", type=int, default=1000, help="length of the timed reverse chain")
     ap.add_argument("--no-sampling", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="keep weight-gradient GEMMs on the main stream")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -243,7 +244,7 @@ def main():
     x_dev = host_x.to(dev)
     hook = parallel.FlatGradAllReduce() if world > 1 else None
 
-    step = eng.capture_train_step((B, 3, RES, RES), grad_hook=hook)
+    step = eng.capture_train_step((B, 3, RES, RES), grad_hook=hook, overlap_wgrad=not args.no_overlap)
     kernels_per_step = step.state["kernels_per_step"]  # this library's kernels inside one captured step
 
     def barrier():

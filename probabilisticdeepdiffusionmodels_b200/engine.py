@@ -365,10 +365,12 @@ class Engine(_Base):
                             ("test_nll", "nll"), ("test_mse", "MSE")):
             self.log(k_out, nll[k_in])
 
-    def calculate_likelihood(self, x):
-        """Eq. (5) of DDPM in bits/dim (src/engine.py:417-435)."""
+    def calculate_likelihood(self, x, t_batch=1):
+        """Eq. (5) of DDPM in bits/dim (src/engine.py:417-435).  ``t_batch`` > 1 (extension) evaluates that
+        many timesteps per UNet forward by folding t into the batch dimension (the T-1 terms are independent); the
+        default reproduces the reference's one-forward-per-t loop and its noise draw order."""
         L_0 = self._calculate_L_0(x)
-        L_intermediate_list, MSE_list = self._calculate_L_intermediate(x)
+        L_intermediate_list, MSE_list = self._calculate_L_intermediate(x, t_batch)
         L_T = self._calculate_L_T(x)
         L_intermediate = torch.sum(torch.stack(L_intermediate_list), dim=0)
         return {"MSE": torch.mean(torch.stack(MSE_list)), "MSE_list": MSE_list, "L_0": torch.mean(L_0, dim=0),
@@ -385,10 +387,26 @@ class Engine(_Base):
         """KL(q(x_T|x_0) || N(0, I)) (src/engine.py:437-444)"""
         return self._vlb(x, None, None, None, 2)
 
-    def _calculate_L_intermediate(self, x0) -> Tuple[List[torch.Tensor], List[torch.Tensor]]:
+    def _calculate_L_intermediate(self, x0, t_batch=1) -> Tuple[List[torch.Tensor], List[torch.Tensor]]:
         """sum_t KL(q(x_{t-1}|x_t,x_0) || p(x_{t-1}|x_t)), fixed variance (src/engine.py:446-475)"""
         L_list, MSE_list = [], []
         ones = torch.ones(x0.shape[0], dtype=torch.int64, device=self.device)
+        if t_batch > 1:
+            B = x0.shape[0]
+            steps = list(range(2, self.diffusion_steps + 1))
+            for i in range(0, len(steps), t_batch):
+                chunk = steps[i: i + t_batch]
+                t = torch.tensor(chunk, dtype=torch.int64, device=self.device).repeat_interleave(B)
+                xr = x0.repeat(len(chunk), 1, 1, 1)
+                noise = torch.randn_like(xr)
+                x_t = self.get_q_t(xr, noise, t)
+                out = self.model(x_t, t)
+                eps = out[:, : x0.shape[1]].contiguous() if self.learn_sigma else out
+                kl = self._vlb(xr, x_t, eps, t, 0).view(len(chunk), B)
+                mse = torch.pow(eps - noise, 2).view(len(chunk), B, *x0.shape[1:])
+                L_list.extend(kl.unbind(0))
+                MSE_list.extend(mse.unbind(0))
+            return L_list, MSE_list
         for t_step in range(2, self.diffusion_steps + 1):
             t = ones * t_step
             noise = torch.randn_like(x0)
@@ -492,7 +510,7 @@ class Engine(_Base):
         per = self.per_sample_loss(self.model(x_t, t), noise, x, x_t, t)
         return (torch.sum(weights * per) if weights is not None else torch.mean(per)), per
 
-    def capture_train_step(self, batch_shape, optimizer=None, grad_hook=None):
+    def capture_train_step(self, batch_shape, optimizer=None, grad_hook=None, overlap_wgrad=True):
         """Capture one optimisation step (t ~ U{1..T}, eps ~ N(0,1) drawn inside the graph, loss, backward,
         optional ``grad_hook`` (e.g. the data-parallel all-reduce), Adam, EMA) as a CUDA graph.
         Returns ``step(x) -> loss`` replaying it on a static input buffer."""
@@ -508,7 +526,11 @@ class Engine(_Base):
             t = torch.randint(1, self.diffusion_steps + 1, (batch_shape[0],), device=dev)
             noise = torch.randn_like(st["x"])
             loss, per = self.loss_on(st["x"], t, noise)
-            loss.backward()
+            if overlap_wgrad:
+                with ops.overlap_wgrad():  # weight-gradient GEMMs on a side stream, joined before the optimiser
+                    loss.backward()
+            else:
+                loss.backward()
             return loss, per, t
 
         def body():

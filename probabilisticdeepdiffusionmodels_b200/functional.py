@@ -120,8 +120,11 @@ def tap_gemm(x, wp, taps, B, H, W, *, bias=None, bcast=None, residual=None, out=
     return out
 
 
-def tap_wgrad(x, dy, taps, B, H, W, cin, cout, w_shape, accumulate_into=None):
-    """dw[n, c, tap] = sum_pixels dy[b,h,w,n] * x[b+db, h+dh, w+dw, c]  -> fp32 tensor of shape w_shape."""
+def tap_wgrad(x, dy, taps, B, H, W, cin, cout, w_shape, accumulate_into=None, launch_stream=None, keep=None):
+    """dw[n, c, tap] = sum_pixels dy[b,h,w,n] * x[b+db, h+dh, w+dw, c]  -> fp32 tensor of shape w_shape.
+
+    ``launch_stream``: enqueue on that stream instead of the current one (buffers are still allocated from the
+    current stream's pool; the caller keeps them alive through ``keep`` until it has joined the streams)."""
     L.require_device(x)
     _chk(x, bf16)
     _chk(dy, bf16)
@@ -134,7 +137,10 @@ def tap_wgrad(x, dy, taps, B, H, W, cin, cout, w_shape, accumulate_into=None):
     p.accumulate = 1 if accumulate_into is not None else 0
     nbytes = L.load().pddm_conv2d_wgrad_workspace(C.byref(p))
     ws = _ws(nbytes, x.device)
-    L.call("pddm_conv2d_wgrad", C.byref(p), L.ptr(ws), C.c_size_t(ws.numel()), L.stream())
+    st = L.stream() if launch_stream is None else C.c_void_p(launch_stream.cuda_stream)
+    L.call("pddm_conv2d_wgrad", C.byref(p), L.ptr(ws), C.c_size_t(ws.numel()), st)
+    if keep is not None:
+        keep.extend((ws, dw, x, dy))
     return dw
 
 

@@ -51,6 +51,37 @@ def _packed(w, mode):
     return ent[1]
 
 
+_OVERLAP = {"on": 0, "side": None, "keep": []}
+
+
+@contextlib.contextmanager
+def overlap_wgrad():
+    """Run every conv weight-gradient GEMM of the enclosed backward pass on a side stream.
+
+    A weight gradient is a leaf of the backward graph (only the optimiser consumes it), while the data gradient
+    feeds the next GroupNorm backward; the wgrad kernel is TMA/tensor bound and light on registers, the GroupNorm /
+    reduction kernels are LSU/L2 bound, so they co-reside on the SMs.  The streams are joined on exit (also valid
+    inside CUDA-graph capture: fork and join become graph edges).  Requires ``.grad is None`` on entry."""
+    cur = torch.cuda.current_stream()
+    if _OVERLAP["side"] is None or _OVERLAP["side"].device != cur.device:
+        _OVERLAP["side"] = torch.cuda.Stream(device=cur.device)
+    _OVERLAP["on"] += 1
+    try:
+        yield
+    finally:
+        _OVERLAP["on"] -= 1
+        torch.cuda.current_stream().wait_stream(_OVERLAP["side"])
+        _OVERLAP["keep"].clear()
+
+
+def _wgrad(xin, dy, taps, B, H, W, Cin, Cout, shape):
+    if not _OVERLAP["on"]:
+        return F.tap_wgrad(xin, dy, taps, B, H, W, Cin, Cout, shape)
+    side = _OVERLAP["side"]
+    side.wait_stream(torch.cuda.current_stream())  # dy / xin are ready
+    return F.tap_wgrad(xin, dy, taps, B, H, W, Cin, Cout, shape, launch_stream=side, keep=_OVERLAP["keep"])
+
+
 class WeightArena:
     """All bf16 weight packs of a model in one flat buffer, refreshed by ONE kernel launch per optimiser step.
 
@@ -183,7 +214,7 @@ def conv2d_bwd(dy: Tensor, xin: Tensor, weight: Tensor, stride: int, upsample: b
         taps = F.taps_stride2(B)
     else:
         taps = F.taps_3x3() if k == 3 else F.taps_1x1()
-    dw = F.tap_wgrad(xin, dy, taps, B, H, W, Cin, Cout, tuple(weight.shape))
+    dw = _wgrad(xin, dy, taps, B, H, W, Cin, Cout, tuple(weight.shape))
     dbias = F.colsum(dy, Cout) if need_dbias else _empty(dy)
     dbcast = F.colsum_per_sample(dy) if need_dbcast else _empty(dy)
     dx = _empty(dy)

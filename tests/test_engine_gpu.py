@@ -142,3 +142,26 @@ def test_captured_train_step_learns():
     assert all(np.isfinite(losses))
     assert np.mean(losses[-5:]) < np.mean(losses[:5])
     assert any(not torch.equal(a, b) for a, b in zip(before, eng.model.parameters()))
+
+
+def test_nll_eval_batched_over_t_matches_sequential(monkeypatch):
+    """Folding timesteps into the batch gives the same per-t KL terms when fed the same noise."""
+    eng = make_engine("cosine", steps=12)
+    eng.eval()
+    x0 = (torch.randint(0, 256, (3, 1, 28, 28)).float() / 127.5 - 1).cuda()
+    noise_bank = torch.randn(11, 3, 1, 28, 28, device="cuda")
+    calls = {"i": 0}
+
+    def seq_noise(x, **k):
+        n = noise_bank[calls["i"]]
+        calls["i"] += 1
+        return n.clone()
+
+    monkeypatch.setattr(torch, "randn_like", seq_noise)
+    with torch.no_grad():
+        seq, _ = eng._calculate_L_intermediate(x0, 1)
+    monkeypatch.setattr(torch, "randn_like", lambda x, **k: noise_bank[: x.shape[0] // 3].reshape(x.shape).clone())
+    with torch.no_grad():
+        bat, _ = eng._calculate_L_intermediate(x0, 11)
+    assert len(seq) == len(bat) == 11
+    torch.testing.assert_close(torch.stack(bat), torch.stack(seq), rtol=2e-3, atol=1e-5)
