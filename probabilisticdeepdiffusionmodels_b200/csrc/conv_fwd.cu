@@ -9,7 +9,7 @@
 //               shared memory.
 //   warp 0      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BLOCK_N x 16, bf16 -> fp32),
 //               accumulators double-buffered in tensor memory so the epilogue of tile i overlaps the main loop of
-//               tile i+1; two 128-row sub-tiles may share one weight tile.
+//               tile i+1.
 //   warps 4..7  epilogue: tcgen05.ld 32 lanes x 32 columns, + bias + per-sample broadcast (timestep embedding)
 //               + residual, convert, 128-bit stores.
 // Pipelines: smem full/empty mbarrier ring (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue).
@@ -32,7 +32,7 @@ struct ConvKArgs {
   int tap_db[PDDM_MAX_TAPS], tap_dh[PDDM_MAX_TAPS], tap_dw[PDDM_MAX_TAPS], tap_w[PDDM_MAX_TAPS];
   int out_H, out_W, out_sh, out_sw, out_oh, out_ow;
   int stages, a_slot_bytes, a_tx_bytes, b_bytes;
-  int mt;    // M sub-tiles (of 128 rows) per CTA tile sharing one B tile: 1 or 2
+  int mt;    // 128-row M sub-tiles per CTA tile sharing one weight tile (1 or 2): 8 UMMAs per barrier round trip
   int nacc;  // accumulator stages in TMEM (2 = epilogue overlaps the next tile's main loop)
   int dbg;   // PDDM_CONV_DBG experiment bits: 1 = empty epilogue, 2 = no A loads, 4 = no MMAs, 8 = no B loads
   uint32_t idesc, layout_type, sbo_bytes, tmem_cols;
@@ -49,19 +49,21 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const __grid_constant__ ConvKArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int stage_bytes = a.mt * a.a_slot_bytes + a.b_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.stages * stage_bytes);
+  const int mt = a.mt;
+  const int stage_bytes = mt * a.a_slot_bytes + a.b_bytes;
+  const int nstages = a.stages, nacc = a.nacc, dbg = a.dbg;
+  const int m_tiles = (a.m_tiles + mt - 1) / mt;  // CTA tiles along M (mt sub-tiles each)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nstages * stage_bytes);
   uint64_t* full_bar = bars;                      // [stages]
   uint64_t* empty_bar = bars + kMaxStages;        // [stages]
   uint64_t* tmem_full = bars + 2 * kMaxStages;    // [2]
   uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;  // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
-  float* smem_add = reinterpret_cast<float*>(smem + a.stages * stage_bytes + 512);
+  float* smem_add = reinterpret_cast<float*>(smem + nstages * stage_bytes + 512);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_super = (a.m_tiles + a.mt - 1) / a.mt;  // CTA tiles along M (mt sub-tiles each)
-  const int total_tiles = m_super * a.n_tiles;
+  const int total_tiles = m_tiles * a.n_tiles;
   const int total_kb = a.ntaps * a.kblocks_per_tap;
 
   if (warp == 1 && lane == 0) {
@@ -69,7 +71,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tma_prefetch_desc(&tmB);
   }
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < a.stages; ++s) {
+    for (int s = 0; s < nstages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -87,86 +89,120 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   if (warp >= 1 && warp <= 3) {
     // ---------------------------------------------------------------- TMA producers (3 single-lane issuers)
-    // Issuing one K-block (barrier wait + expect_tx + a 4-D and a 2-D bulk-tensor copy) costs ~700 cycles of
-    // issue latency on one thread, more than the 256-512 cycles of tensor work it feeds; K-blocks are therefore
-    // dealt round-robin to three producer warps.  Stage and parity follow from the global K-block index.
-    // (the loops run warp-uniformly and only the issue is predicated on one elected lane: inside a divergent
-    //  `if (lane == 0)` region the compiler has to wrap every UTMALDG / UTCHMMA / SYNCS operand in a
-    //  uniform-register waterfall loop, which costs ~100-200 cycles per instruction)
-    {
-      const int pid = warp - 1;
-      int g = 0;  // global K-block index of this CTA
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int ms = tile % m_super, n_tile = tile / m_super;
-        int b0[2], h0[2], w0[2];
-        for (int hf = 0; hf < a.mt; ++hf) {
-          const int m_tile = ms * a.mt + hf;  // may run past m_tiles: coordinates then fall outside -> zero fill
-          b0[hf] = (m_tile / (a.tiles_w * a.tiles_h)) * a.BB;
-          h0[hf] = ((m_tile / a.tiles_w) % a.tiles_h) * a.BH;
-          w0[hf] = (m_tile % a.tiles_w) * a.BW;
-        }
-        for (int tap = 0; tap < a.ntaps; ++tap) {
-          for (int kc = 0; kc < a.kblocks_per_tap; ++kc, ++g) {
-            if (g % kNumProducers != pid) continue;
-            const int stage = g % a.stages;
-            const uint32_t phase = (g / a.stages) & 1;
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            if (elect_one()) {
-              mbar_expect_tx(&full_bar[stage],
-                             ((a.dbg & 2) ? 0 : a.mt * a.a_tx_bytes) + ((a.dbg & 8) ? 0 : a.b_bytes));
-              uint8_t* sa = smem + stage * stage_bytes;
-              for (int hf = 0; hf < a.mt && !(a.dbg & 2); ++hf)
-                tma_load_4d(sa + hf * a.a_slot_bytes, &tmA, &full_bar[stage], kc * a.bk, w0[hf] + a.tap_dw[tap],
-                            h0[hf] + a.tap_dh[tap], b0[hf] + a.tap_db[tap]);
-              if (!(a.dbg & 8))
-                tma_load_2d(sa + a.mt * a.a_slot_bytes, &tmB, &full_bar[stage],
-                            (a.tap_w[tap] * a.kblocks_per_tap + kc) * a.bk, n_tile * a.block_n);
-            }
-            __syncwarp();
+    // Issuing one K-block (barrier wait + expect_tx + a 4-D and a 2-D bulk-tensor copy) costs several hundred
+    // cycles of issue latency on one thread, more than the 256-512 cycles of tensor work it feeds; K-blocks are
+    // therefore dealt round-robin to three producer warps, each walking its own (tile, tap, channel-block,
+    // stage, parity) counters.  The loops run warp-uniformly and only the issue is predicated on one elected
+    // lane: inside a divergent `if (lane == 0)` region the compiler wraps every UTMALDG / SYNCS operand in a
+    // uniform-register waterfall loop (~100-200 cycles per instruction).
+    const int pid = warp - 1;
+    const int kpt = a.kblocks_per_tap, ntaps = a.ntaps, bk = a.bk, block_n = a.block_n;
+    const int tiles_w = a.tiles_w, tiles_h = a.tiles_h, BW = a.BW, BH = a.BH, BB = a.BB;
+    const uint32_t tx_bytes = ((dbg & 2) ? 0 : mt * a.a_tx_bytes) + ((dbg & 8) ? 0 : a.b_bytes);
+    const uint32_t a_slot = a.a_slot_bytes;
+    int stage = pid % nstages;
+    uint32_t phase = (pid / nstages) & 1;
+    int kb = pid;  // K-block index inside the current tile
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_tile = (tile % m_tiles) * mt, n_tile = tile / m_tiles;
+      const int b0 = (m_tile / (tiles_w * tiles_h)) * BB;
+      const int h0 = ((m_tile / tiles_w) % tiles_h) * BH;
+      const int w0 = (m_tile % tiles_w) * BW;
+      // second sub-tile (mt == 2); past the last tile its coordinates fall outside the tensor -> zero fill
+      const int b1 = ((m_tile + 1) / (tiles_w * tiles_h)) * BB;
+      const int h1 = (((m_tile + 1) / tiles_w) % tiles_h) * BH;
+      const int w1 = ((m_tile + 1) % tiles_w) * BW;
+      const int n0 = n_tile * block_n;
+      int tap = kb / kpt, kc = kb - tap * kpt;
+      while (kb < total_kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
+          uint8_t* sa = smem + stage * stage_bytes;
+          mbar_expect_tx(&full_bar[stage], tx_bytes);
+          if (!(dbg & 2)) {
+            tma_load_4d(sa, &tmA, &full_bar[stage], kc * bk, w0 + a.tap_dw[tap], h0 + a.tap_dh[tap],
+                        b0 + a.tap_db[tap]);
+            if (mt == 2)
+              tma_load_4d(sa + a_slot, &tmA, &full_bar[stage], kc * bk, w1 + a.tap_dw[tap], h1 + a.tap_dh[tap],
+                          b1 + a.tap_db[tap]);
           }
+          if (!(dbg & 8))
+            tma_load_2d(sa + mt * a_slot, &tmB, &full_bar[stage], (a.tap_w[tap] * kpt + kc) * bk, n0);
+        }
+        __syncwarp();
+        kb += kNumProducers;
+        kc += kNumProducers;
+        while (kc >= kpt) {
+          kc -= kpt;
+          ++tap;
+        }
+        stage += kNumProducers;
+        while (stage >= nstages) {
+          stage -= nstages;
+          phase ^= 1;
         }
       }
+      kb -= total_kb;  // carry the round-robin position into the next tile
     }
   } else if (warp == 0) {
     // ---------------------------------------------------------------- MMA issuer (warp-uniform loop, one lane issues)
-    {
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    // Everything the loop needs is hoisted into registers: per K-block it is one barrier wait, one 64-bit add per
+    // operand descriptor, the UMMAs and the commit.  (A single thread's dependent-instruction latency, not the
+    // tensor pipe, bounds this loop when it is written carelessly: ~70 SASS instructions per K-block measured
+    // 0.32 us against 0.135 us of tensor work at N=128.)
+    const uint64_t desc0 = make_smem_desc(smem_u32(smem), 16, a.sbo_bytes, a.layout_type);
+    const uint32_t stage_d = static_cast<uint32_t>(stage_bytes) >> 4;  // descriptor address field counts 16 B
+    const uint32_t a_slot_d = static_cast<uint32_t>(a.a_slot_bytes) >> 4;
+    const uint32_t b_off_d = mt * a_slot_d;
+    const uint32_t idesc = a.idesc;
+    const bool k64 = a.bk == 64;
+    const bool no_mma = dbg & 4;
+    const uint32_t block_n = a.block_n;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * mt * block_n;
+      for (int kb = 0; kb < total_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * a.mt * a.block_n;
-        for (int kb = 0; kb < total_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-            const uint32_t sb = sa + a.mt * a.a_slot_bytes;
-            const uint64_t bdesc = make_smem_desc(sb, 16, a.sbo_bytes, a.layout_type);
-            const int ksteps = a.bk >> 4;
-            for (int hf = 0; hf < a.mt && !(a.dbg & 4); ++hf) {  // the sub-tiles reuse the B tile already in smem
-              const uint64_t adesc = make_smem_desc(sa + hf * a.a_slot_bytes, 16, a.sbo_bytes, a.layout_type);
-              for (int k = 0; k < ksteps; ++k) {
-                // advance 16 elements (32 B) along K inside the swizzled row: +2 in the (addr >> 4) field
-                umma_bf16(d_tmem + hf * a.block_n, adesc + 2 * k, bdesc + 2 * k, a.idesc, (kb | k) != 0);
+        if (elect_one()) {
+          const uint64_t adesc = desc0 + static_cast<uint64_t>(stage * stage_d);
+          const uint64_t bdesc = adesc + b_off_d;
+          if (!no_mma) {
+            // advance 16 elements (32 B) along K inside the swizzled row: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, adesc, bdesc, idesc, kb != 0);
+            umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
+            if (k64) {
+              umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
+              umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
+            }
+            if (mt == 2) {  // the second sub-tile reuses the weight tile already in shared memory
+              const uint64_t adesc1 = adesc + a_slot_d;
+              umma_bf16(d_tmem + block_n, adesc1, bdesc, idesc, kb != 0);
+              umma_bf16(d_tmem + block_n, adesc1 + 2, bdesc + 2, idesc, 1);
+              if (k64) {
+                umma_bf16(d_tmem + block_n, adesc1 + 4, bdesc + 4, idesc, 1);
+                umma_bf16(d_tmem + block_n, adesc1 + 6, bdesc + 6, idesc, 1);
               }
             }
-            umma_commit(&empty_bar[stage]);
           }
-          __syncwarp();
-          if (++stage == a.stages) {
-            stage = 0;
-            phase ^= 1;
-          }
+          umma_commit(&empty_bar[stage]);
         }
-        if (elect_one()) umma_commit(&tmem_full[acc]);
         __syncwarp();
-        if (++acc == a.nacc) {
-          acc = 0;
-          acc_phase ^= 1;
+        if (++stage == nstages) {
+          stage = 0;
+          phase ^= 1;
         }
+      }
+      if (elect_one()) umma_commit(&tmem_full[acc]);
+      __syncwarp();
+      if (++acc == nacc) {
+        acc = 0;
+        acc_phase ^= 1;
       }
     }
   } else if (warp >= 4) {
@@ -181,9 +217,9 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const bool has_add = (a.bias != nullptr) || (a.bcast != nullptr);
     const bool stage_add = has_add && a.BB <= kMaxAddRows;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-     const int ms = tile % m_super, n_tile = tile / m_super;
-     for (int hf = 0; hf < a.mt; ++hf) {
-      const int m_tile = ms * a.mt + hf;
+     const int n_tile = tile / m_tiles;
+     for (int hf = 0; hf < mt; ++hf) {
+      const int m_tile = (tile % m_tiles) * mt + hf;
       const int tw = m_tile % a.tiles_w;
       const int th = (m_tile / a.tiles_w) % a.tiles_h;
       const int tb = m_tile / (a.tiles_w * a.tiles_h);
@@ -225,7 +261,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       if (hf == 0) mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (acc * a.mt + hf) * a.block_n;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (acc * mt + hf) * a.block_n;
       uint32_t r[2][32];
       tmem_ld32(taddr, r[0]);
       for (int cp = 0; cp < nchunks; cp += 2) {
@@ -244,7 +280,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
           const int n0 = nbase + c * 32;
-          if (valid && n0 < a.Cout && !(a.dbg & 1)) {
+          if (valid && n0 < a.Cout && !(dbg & 1)) {
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[ci][j]);
@@ -303,12 +339,12 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
        }
       }
-     }  // sub-tiles
+     }
       // all of this warp's TMEM reads have completed (last tmem_ld_wait): hand the accumulator back
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      if (++acc == a.nacc) {
+      if (++acc == nacc) {
         acc = 0;
         acc_phase ^= 1;
       }
@@ -397,10 +433,11 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
   a.a_tx_bytes = a.BW * a.BH * a.BB * swz;
   a.b_bytes = a.block_n * swz;
   a.idesc = make_idesc_bf16(128, a.block_n, 0, 0);
-  // Two 128-row sub-tiles per CTA tile share each B (weight) tile: the kernel is bound by the L2 -> shared-memory
-  // fill rate (~42 B/clk/SM), and this cuts the bytes per MMA by 25-33%.  Used when it still leaves >= 1 full wave.
-  a.mt = 1;  // measured: sharing B across two sub-tiles does not pay (the kernel is issue-latency, not L2, bound)
-  if (getenv("PDDM_CONV_MT")) a.mt = atoi(getenv("PDDM_CONV_MT")) == 2 ? 2 : 1;
+  // Two 128-row sub-tiles can share one weight tile (8 UMMAs per barrier round trip, 25% fewer bytes into smem).
+  // Measured on B200 it does not pay: a 128x128x16 UMMA costs ~105 cycles against ~144 for 128x256x16 whatever the
+  // issue pattern, and the 256-row tiles lose more to wave quantisation than they gain.  Kept as an experiment knob.
+  a.mt = 1;
+  if (getenv("PDDM_CONV_MT")) a.mt = atoi(getenv("PDDM_CONV_MT")) == 2 && a.block_n <= 128 ? 2 : 1;
   a.nacc = (2 * a.mt * a.block_n <= 512) ? 2 : 1;
   a.dbg = getenv("PDDM_CONV_DBG") ? atoi(getenv("PDDM_CONV_DBG")) : 0;
   uint32_t cols = 32;

@@ -47,6 +47,29 @@ static void taps3x3(Case& c) {
     }
 }
 
+template <class F>
+static float time_in_graph(F launch, cudaEvent_t e0, cudaEvent_t e1) {
+  cudaStream_t s;
+  cudaStreamCreate(&s);
+  cudaGraph_t g;
+  cudaGraphExec_t ge;
+  cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+  for (int i = 0; i < 10; ++i) launch(s);
+  cudaStreamEndCapture(s, &g);
+  cudaGraphInstantiate(&ge, g, 0);
+  cudaGraphLaunch(ge, s);
+  cudaEventRecord(e0, s);
+  for (int i = 0; i < 3; ++i) cudaGraphLaunch(ge, s);
+  cudaEventRecord(e1, s);
+  cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaGraphExecDestroy(ge);
+  cudaGraphDestroy(g);
+  cudaStreamDestroy(s);
+  return ms / 30;
+}
+
 static int run_case(const Case& c) {
   const size_t nx = (size_t)c.x_NB * c.H * c.W * c.ldx;
   const size_t nw = (size_t)c.Cout * c.ntaps * c.Cin;
@@ -142,15 +165,11 @@ static int run_case(const Case& c) {
     const double tol = (c.y_dtype == PDDM_BF16 ? 1e-2 : 2e-4) * fmax(1.0, fabs(yref[i]));
     if (!(err <= tol)) ++bad;
   }
-  // forward timing
+  // forward timing: 10 launches captured in a CUDA graph (the product path replays graphs, and direct launches of
+  // the small shapes would time the host-side tensor-map encode instead of the kernel)
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
-  for (int i = 0; i < 3; ++i) pddm_conv2d_fwd(&p, nullptr);
-  cudaEventRecord(e0);
-  for (int i = 0; i < 10; ++i) pddm_conv2d_fwd(&p, nullptr);
-  cudaEventRecord(e1);
-  CK(cudaEventSynchronize(e1));
-  float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 10;
+  float ms = time_in_graph([&](cudaStream_t s) { pddm_conv2d_fwd(&p, s); }, e0, e1);
   const double fl = 2.0 * c.B * c.H * c.W * c.Cout * c.ntaps * c.Cin;
   printf("[%s] fwd   %-28s maxerr=%.3e maxref=%.2f bad=%zu  %.1f us  %.1f TF/s\n", bad ? "FAIL" : " ok ", c.name, maxerr,
          maxref, bad, ms * 1e3, fl / ms * 1e-9);
@@ -212,12 +231,7 @@ static int run_case(const Case& c) {
             werr = fmax(werr, fabs(v - r));
             if (!(fabs(v - r) <= 2e-3 * fmax(1.0, fabs(r)) + 1e-3)) ++nb;
           }
-      for (int i = 0; i < 2; ++i) pddm_conv2d_wgrad(&q, ws, wsb, nullptr);
-      cudaEventRecord(e0);
-      for (int i = 0; i < 5; ++i) pddm_conv2d_wgrad(&q, ws, wsb, nullptr);
-      cudaEventRecord(e1);
-      CK(cudaEventSynchronize(e1));
-      cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
+      ms = time_in_graph([&](cudaStream_t s) { pddm_conv2d_wgrad(&q, ws, wsb, s); }, e0, e1);
       printf("[%s] wgrad %-28s layout=%d maxerr=%.3e maxref=%.2f bad=%zu ws=%.1fMB  %.1f us  %.1f TF/s\n",
              nb ? "FAIL" : " ok ", c.name, layout, werr, wmax, nb, wsb / 1e6, ms * 1e3, fl / ms * 1e-9);
       wbad += nb != 0;
