@@ -86,79 +86,88 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   if (warp >= 1 && warp <= 3) {
     // TMA producers: a K-block needs 2 + n_chunks bulk-tensor copies (~200 cycles of issue latency each on one
     // thread), far more than the 512 cycles of tensor work it feeds, so K-blocks are dealt round-robin to three
-    // single-lane producers; stage and parity follow from the global K-block index.
+    // single-lane producers, each walking its own (item, K-block, stage, parity) counters.
     // (warp-uniform loop, issue predicated on one elected lane: see conv_fwd.cu)
-    {
-      const int pid = warp - 1;
-      int g = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        int tap, m_tile, n_tile, split;
-        decode(item, tap, m_tile, n_tile, split);
-        const int kb0 = split * a.kb_per_split;
-        const int kb1 = min(kb0 + a.kb_per_split, a.k_blocks);
-        for (int kb = kb0; kb < kb1; ++kb, ++g) {
-          if (g % 3 != pid) continue;
-          const int stage = g % a.stages;
-          const uint32_t phase = (g / a.stages) & 1;
-          const int tw = kb % a.tiles_w;
-          const int th = (kb / a.tiles_w) % a.tiles_h;
-          const int tb = kb / (a.tiles_w * a.tiles_h);
-          const int b0 = tb * a.BB, h0 = th * a.BH, w0 = tw * a.BW;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (elect_one()) {
-            mbar_expect_tx(&full_bar[stage], a.tx_bytes);
-            uint8_t* sa = smem + stage * stage_bytes;
-            tma_load_4d(sa, &tmDY, &full_bar[stage], m_tile * 128, w0, h0, b0);
-            tma_load_4d(sa + kChunkBytes, &tmDY, &full_bar[stage], m_tile * 128 + 64, w0, h0, b0);
-            for (int c = 0; c < a.n_chunks; ++c)
-              tma_load_4d(sa + a_bytes + c * kChunkBytes, &tmX, &full_bar[stage], n_tile * a.block_n + c * 64,
-                          w0 + a.tap_dw[tap], h0 + a.tap_dh[tap], b0 + a.tap_db[tap]);
-          }
-          __syncwarp();
+    const int pid = warp - 1;
+    const int nstages = a.stages, n_chunks = a.n_chunks, block_n = a.block_n;
+    const int tiles_w = a.tiles_w, tiles_h = a.tiles_h, BB = a.BB, BH = a.BH, BW = a.BW;
+    const uint32_t tx_bytes = a.tx_bytes;
+    int stage = pid % nstages;
+    uint32_t phase = (pid / nstages) & 1;
+    int skip = pid;  // K-blocks of the current item that belong to the other producers before ours
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      int tap, m_tile, n_tile, split;
+      decode(item, tap, m_tile, n_tile, split);
+      const int kb0 = split * a.kb_per_split;
+      const int kb1 = min(kb0 + a.kb_per_split, a.k_blocks);
+      const int dw = a.tap_dw[tap], dh = a.tap_dh[tap], db = a.tap_db[tap];
+      int kb = kb0 + skip;
+      for (; kb < kb1; kb += 3) {
+        const int tw = kb % tiles_w;
+        const int th = (kb / tiles_w) % tiles_h;
+        const int tb = kb / (tiles_w * tiles_h);
+        const int b0 = tb * BB, h0 = th * BH, w0 = tw * BW;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&full_bar[stage], tx_bytes);
+          uint8_t* sa = smem + stage * stage_bytes;
+          tma_load_4d(sa, &tmDY, &full_bar[stage], m_tile * 128, w0, h0, b0);
+          tma_load_4d(sa + kChunkBytes, &tmDY, &full_bar[stage], m_tile * 128 + 64, w0, h0, b0);
+          for (int c = 0; c < n_chunks; ++c)
+            tma_load_4d(sa + a_bytes + c * kChunkBytes, &tmX, &full_bar[stage], n_tile * block_n + c * 64, w0 + dw,
+                        h0 + dh, b0 + db);
+        }
+        __syncwarp();
+        stage += 3;
+        while (stage >= nstages) {
+          stage -= nstages;
+          phase ^= 1;
         }
       }
+      skip = kb - kb1;  // carry the round-robin position into the next item
     }
   } else if (warp == 0) {
-    {
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        int tap, m_tile, n_tile, split;
-        decode(item, tap, m_tile, n_tile, split);
-        const int kb0 = split * a.kb_per_split;
-        const int kb1 = min(kb0 + a.kb_per_split, a.k_blocks);
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    // MMA issuer: loop state hoisted into registers (see conv_fwd.cu)
+    const int nstages = a.stages;
+    // MN-major SW128: LBO = distance between 64-channel chunks, SBO = 8 pixel rows * 128 B
+    const uint64_t adesc0 = make_smem_desc(smem_u32(smem), kChunkBytes, 1024, kLayoutSW128);
+    const uint32_t stage_d = static_cast<uint32_t>(stage_bytes) >> 4, b_off_d = static_cast<uint32_t>(a_bytes) >> 4;
+    const uint32_t idesc = a.idesc, block_n = a.block_n;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      int tap, m_tile, n_tile, split;
+      decode(item, tap, m_tile, n_tile, split);
+      const int kb0 = split * a.kb_per_split;
+      const int kb1 = min(kb0 + a.kb_per_split, a.k_blocks);
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * block_n;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * a.block_n;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-            const uint32_t sb = sa + a_bytes;
-            // MN-major SW128: LBO = distance between 64-channel chunks, SBO = 8 pixel rows * 128 B
-            const uint64_t adesc = make_smem_desc(sa, kChunkBytes, 1024, kLayoutSW128);
-            const uint64_t bdesc = make_smem_desc(sb, kChunkBytes, 1024, kLayoutSW128);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              // 16 pixel rows per MMA = 2048 B = 128 in the (addr >> 4) field
-              umma_bf16(d_tmem, adesc + 128 * k, bdesc + 128 * k, a.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            }
-            umma_commit(&empty_bar[stage]);
-          }
-          __syncwarp();
-          if (++stage == a.stages) {
-            stage = 0;
-            phase ^= 1;
-          }
+        if (elect_one()) {
+          const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * stage_d);
+          const uint64_t bdesc = adesc + b_off_d;
+          // 16 pixel rows per MMA = 2048 B = 128 in the (addr >> 4) field
+          umma_bf16(d_tmem, adesc, bdesc, idesc, kb > kb0 ? 1u : 0u);
+          umma_bf16(d_tmem, adesc + 128, bdesc + 128, idesc, 1u);
+          umma_bf16(d_tmem, adesc + 256, bdesc + 256, idesc, 1u);
+          umma_bf16(d_tmem, adesc + 384, bdesc + 384, idesc, 1u);
+          umma_commit(&empty_bar[stage]);
         }
-        if (elect_one()) umma_commit(&tmem_full[acc]);
         __syncwarp();
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        if (++stage == nstages) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
+      if (elect_one()) umma_commit(&tmem_full[acc]);
+      __syncwarp();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else if (warp >= 4) {
     const int q = warp & 3;

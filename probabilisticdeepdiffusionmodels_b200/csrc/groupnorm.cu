@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include "host_common.h"
+#include "ptx.cuh"
 
 namespace pddm {
 
@@ -53,6 +54,20 @@ __device__ __forceinline__ float ld_peer_smem(const float* local_ptr, int rank) 
   float v;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(rank));
   asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(raddr) : "memory");
+  return v;
+}
+
+// sum of one shared-memory float over the S CTAs of the cluster, in rank order; the loads are issued back to back
+// (a dependent add after each ld.shared::cluster would serialise ~S remote round trips)
+__device__ __forceinline__ float cluster_fold(const float* local_ptr, int S) {
+  float t[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (k < S) t[k] = ld_peer_smem(local_ptr, k);
+  float v = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (k < S) v += t[k];
   return v;
 }
 
@@ -347,6 +362,343 @@ __global__ void gn_bwd_finalize_kernel(pddm_gn_bwd_params p, const float* __rest
   }
 }
 
+// ------------------------------------------------------------------------------------------------ slab-resident path
+// The common case (bf16 activations, no scale-shift, one sample's slab of rows small enough for shared memory):
+// each CTA of the cluster pulls its slab [rows, C] into shared memory ONCE with 1-D bulk copies (cp.async.bulk +
+// mbarrier complete_tx, chunked so the statistics pass starts on the first chunk while the rest is in flight), and
+// both passes then run out of shared memory.  HBM traffic is the algorithmic minimum -- forward: read x, write y
+// (4 B/element); backward: read x and dy, write dx (6 B/element) -- instead of 6 and 12 B/element for the
+// register-streaming kernels above, and the deep bulk-copy queue keeps enough bytes in flight per SM that the
+// kernel no longer depends on occupancy to cover HBM latency.  A thread owns 8 consecutive channels (one 16-byte
+// shared-memory word per row) and the same rows in both passes, so the slab needs no intra-CTA synchronisation.
+constexpr int CH8 = 8;
+constexpr int kSlabChunks = 8;
+
+struct SlabGeom {
+  int B, HW, C, G, cpg, CV, nlanes, S, rows_per_cta, chunk_rows;
+  int slab_bytes;  // bytes reserved per slab (rows_per_cta * C * 2, rounded up to 128)
+};
+
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+    f[2 * j] = __low2float(h);
+    f[2 * j + 1] = __high2float(h);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 v;
+  v.x = pack_bf16(f[0], f[1]);
+  v.y = pack_bf16(f[2], f[3]);
+  v.z = pack_bf16(f[4], f[5]);
+  v.w = pack_bf16(f[6], f[7]);
+  return v;
+}
+__device__ __forceinline__ void bulk_load_1d(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// issue the chunked bulk copies of this CTA's slab(s); called by one thread after the barriers are initialised
+__device__ __forceinline__ void slab_issue_loads(const SlabGeom& g, int nrows, uint64_t* bars, uint8_t* slab0,
+                                                 const bf16* src0, uint8_t* slab1, const bf16* src1) {
+  const int row_bytes = g.C * 2;
+  for (int ch = 0, r = 0; r < nrows; ++ch, r += g.chunk_rows) {
+    const int rows = min(g.chunk_rows, nrows - r);
+    const uint32_t bytes = static_cast<uint32_t>(rows) * row_bytes;
+    mbar_expect_tx(&bars[ch], src1 ? 2 * bytes : bytes);
+    bulk_load_1d(slab0 + static_cast<size_t>(r) * row_bytes, src0 + static_cast<size_t>(r) * g.C, bytes, &bars[ch]);
+    if (src1)
+      bulk_load_1d(slab1 + static_cast<size_t>(r) * row_bytes, src1 + static_cast<size_t>(r) * g.C, bytes, &bars[ch]);
+  }
+}
+
+__device__ __forceinline__ void ld8(const float* sm, float* r) {
+  const float4 a = *reinterpret_cast<const float4*>(sm), b = *reinterpret_cast<const float4*>(sm + 4);
+  r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+}
+
+template <bool SILU>
+__global__ void __launch_bounds__(256, 2) gn_fwd_slab_kernel(pddm_gn_fwd_params p, SlabGeom g) {
+  extern __shared__ __align__(128) uint8_t smraw[];
+  uint8_t* slab = smraw;
+  float* scratch = reinterpret_cast<float*>(smraw + g.slab_bytes);  // [2][nlanes][C]
+  const int LC = g.nlanes * g.C;
+  float* csum = scratch + 2 * LC;  // [2][C] per-channel sums of this CTA; later the per-channel coefficients a, c
+  float* part = csum + 2 * g.C;    // [G][2] per-group sums of this CTA (read by the cluster peers)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(part + 2 * g.G);
+  const int b = blockIdx.y, s = blockIdx.x;
+  const int cv = threadIdx.x % g.CV, lr = threadIdx.x / g.CV;
+  const int r0 = s * g.rows_per_cta, nrows = min(g.rows_per_cta, g.HW - r0);
+  const size_t gbase = (static_cast<size_t>(b) * g.HW + r0) * g.C;
+  if (threadIdx.x < 32) {
+    if (elect_one()) {
+      for (int i = 0; i < kSlabChunks; ++i) mbar_init(&bars[i], 1);
+      fence_mbar_init();
+      slab_issue_loads(g, nrows, bars, slab, static_cast<const bf16*>(p.x) + gbase, nullptr, nullptr);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  float sum[CH8], sq[CH8];
+#pragma unroll
+  for (int j = 0; j < CH8; ++j) sum[j] = sq[j] = 0.f;
+  for (int ch = 0, c0 = 0; c0 < nrows; ++ch, c0 += g.chunk_rows) {
+    mbar_wait(&bars[ch], 0);
+    const int c1 = min(c0 + g.chunk_rows, nrows);
+    for (int r = c0 + lr; r < c1; r += g.nlanes) {
+      float f[CH8];
+      unpack8(*reinterpret_cast<const uint4*>(slab + (static_cast<size_t>(r) * g.C + cv * CH8) * 2), f);
+#pragma unroll
+      for (int j = 0; j < CH8; ++j) {
+        sum[j] += f[j];
+        sq[j] += f[j] * f[j];
+      }
+    }
+  }
+  {
+    float* d = scratch + lr * g.C + cv * CH8;
+    *reinterpret_cast<float4*>(d) = make_float4(sum[0], sum[1], sum[2], sum[3]);
+    *reinterpret_cast<float4*>(d + 4) = make_float4(sum[4], sum[5], sum[6], sum[7]);
+    *reinterpret_cast<float4*>(d + LC) = make_float4(sq[0], sq[1], sq[2], sq[3]);
+    *reinterpret_cast<float4*>(d + LC + 4) = make_float4(sq[4], sq[5], sq[6], sq[7]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * g.C; i += blockDim.x) {  // fold the row lanes, fixed order
+    const int q = i / g.C, c = i - q * g.C;
+    float v = 0.f;
+    for (int l = 0; l < g.nlanes; ++l) v += scratch[q * LC + l * g.C + c];
+    csum[i] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * g.G; i += blockDim.x) {  // fold the channels of a group
+    const int gi = i >> 1, q = i & 1;
+    float v = 0.f;
+    for (int c = gi * g.cpg; c < (gi + 1) * g.cpg; ++c) v += csum[q * g.C + c];
+    part[i] = v;
+  }
+  if (g.S > 1) cluster_sync_all(); else __syncthreads();
+  // 2G threads fold the group partials over the cluster (rank order) into mean / rstd ...
+  float* gstat = scratch;  // [G][2] (the lane scratch is dead by now)
+  for (int i = threadIdx.x; i < g.G; i += blockDim.x) {
+    const float a = g.S > 1 ? cluster_fold(part + i * 2, g.S) : part[i * 2];
+    const float q = g.S > 1 ? cluster_fold(part + i * 2 + 1, g.S) : part[i * 2 + 1];
+    const float n = static_cast<float>(g.cpg) * g.HW;
+    const float mean = a / n;
+    const float var = fmaxf(q / n - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + p.eps);
+    gstat[i * 2] = mean;
+    gstat[i * 2 + 1] = rstd;
+    if (s == 0) {
+      p.mean[b * g.G + i] = mean;
+      p.rstd[b * g.G + i] = rstd;
+    }
+  }
+  __syncthreads();
+  // ... and every channel thread derives y = x*a + c
+  for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
+    const int gi = c / g.cpg;
+    const float ca = gstat[gi * 2 + 1] * p.gamma[c];
+    csum[c] = ca;
+    csum[g.C + c] = p.beta[c] - gstat[gi * 2] * ca;
+  }
+  __syncthreads();
+  float ca[CH8], cc[CH8];
+  ld8(csum + cv * CH8, ca);
+  ld8(csum + g.C + cv * CH8, cc);
+  bf16* y = static_cast<bf16*>(p.y) + gbase;
+  for (int r = lr; r < nrows; r += g.nlanes) {
+    const size_t off = static_cast<size_t>(r) * g.C + cv * CH8;
+    float f[CH8];
+    unpack8(*reinterpret_cast<const uint4*>(slab + off * 2), f);
+#pragma unroll
+    for (int j = 0; j < CH8; ++j) {
+      const float z = f[j] * ca[j] + cc[j];
+      f[j] = SILU ? z * fast_sigmoid(z) : z;
+    }
+    *reinterpret_cast<uint4*>(y + off) = pack8(f);
+  }
+  if (g.S > 1) cluster_sync_all();  // no CTA may exit while a peer can still read its partials
+}
+
+// backward: slabs of x and dy; pass 1 overwrites the dy slab with dzn (rounded to bf16, as the streaming kernel
+// parks it in dx), pass 2 writes dx.  tot[b][5][C] as above (rows 3,4 are zero without scale-shift).
+template <bool SILU>
+__global__ void __launch_bounds__(256, 2)
+gn_bwd_slab_kernel(pddm_gn_bwd_params p, float* __restrict__ tot, SlabGeom g) {
+  extern __shared__ __align__(128) uint8_t smraw[];
+  uint8_t* slab_x = smraw;
+  uint8_t* slab_d = smraw + g.slab_bytes;
+  float* scratch = reinterpret_cast<float*>(smraw + 2 * g.slab_bytes);  // [3][nlanes][C]
+  const int LC = g.nlanes * g.C;
+  float* part = scratch + 3 * LC;  // [3][C] per-channel sums of this CTA (read by the cluster peers)
+  float* coef = part + 3 * g.C;    // [4][C]: xa, xc, gamma, beta ; later da, db, dc
+  float* sAB = coef + 4 * g.C;     // [2][C]: gamma*A, gamma*Bq over the whole sample
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sAB + 2 * g.C);
+  const int b = blockIdx.y, s = blockIdx.x;
+  const int cv = threadIdx.x % g.CV, lr = threadIdx.x / g.CV;
+  const int r0 = s * g.rows_per_cta, nrows = min(g.rows_per_cta, g.HW - r0);
+  const size_t gbase = (static_cast<size_t>(b) * g.HW + r0) * g.C;
+  if (threadIdx.x < 32) {
+    if (elect_one()) {
+      for (int i = 0; i < kSlabChunks; ++i) mbar_init(&bars[i], 1);
+      fence_mbar_init();
+      slab_issue_loads(g, nrows, bars, slab_x, static_cast<const bf16*>(p.x) + gbase, slab_d,
+                       static_cast<const bf16*>(p.dy) + gbase);
+    }
+    __syncwarp();
+  }
+  for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
+    const int gi = c / g.cpg;
+    const float mu = p.mean[b * g.G + gi], rs = p.rstd[b * g.G + gi];
+    coef[c] = rs;
+    coef[g.C + c] = -mu * rs;
+    coef[2 * g.C + c] = p.gamma[c];
+    coef[3 * g.C + c] = p.beta[c];
+  }
+  __syncthreads();
+  float xa[CH8], xc[CH8], gam[CH8], bet[CH8];
+  ld8(coef + cv * CH8, xa);
+  ld8(coef + g.C + cv * CH8, xc);
+  ld8(coef + 2 * g.C + cv * CH8, gam);
+  ld8(coef + 3 * g.C + cv * CH8, bet);
+  float acc[3][CH8];
+#pragma unroll
+  for (int j = 0; j < CH8; ++j) acc[0][j] = acc[1][j] = acc[2][j] = 0.f;
+  for (int ch = 0, c0 = 0; c0 < nrows; ++ch, c0 += g.chunk_rows) {
+    mbar_wait(&bars[ch], 0);
+    const int c1 = min(c0 + g.chunk_rows, nrows);
+    for (int r = c0 + lr; r < c1; r += g.nlanes) {
+      const size_t off = (static_cast<size_t>(r) * g.C + cv * CH8) * 2;
+      float f[CH8], d[CH8];
+      unpack8(*reinterpret_cast<const uint4*>(slab_x + off), f);
+      unpack8(*reinterpret_cast<const uint4*>(slab_d + off), d);
+#pragma unroll
+      for (int j = 0; j < CH8; ++j) {
+        const float xh = f[j] * xa[j] + xc[j];
+        float dz = d[j];
+        if (SILU) {
+          const float z = xh * gam[j] + bet[j];
+          const float sg = fast_sigmoid(z);
+          dz *= sg * (1.f + z * (1.f - sg));
+        }
+        acc[0][j] += dz;
+        acc[1][j] += dz * xh;
+        acc[2][j] += xh;
+        d[j] = dz;
+      }
+      *reinterpret_cast<uint4*>(slab_d + off) = pack8(d);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    float* d = scratch + q * LC + lr * g.C + cv * CH8;
+    *reinterpret_cast<float4*>(d) = make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
+    *reinterpret_cast<float4*>(d + 4) = make_float4(acc[q][4], acc[q][5], acc[q][6], acc[q][7]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * g.C; i += blockDim.x) {
+    const int q = i / g.C, c = i - q * g.C;
+    float v = 0.f;
+    for (int l = 0; l < g.nlanes; ++l) v += scratch[q * LC + l * g.C + c];
+    part[i] = v;
+  }
+  if (g.S > 1) cluster_sync_all(); else __syncthreads();
+  for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
+    float v[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) v[q] = g.S > 1 ? cluster_fold(part + q * g.C + c, g.S) : part[q * g.C + c];
+    const float gm = coef[2 * g.C + c];
+    sAB[c] = gm * v[0];
+    sAB[g.C + c] = gm * v[1];
+    if (s == 0) {
+      float* t = tot + static_cast<size_t>(b) * 5 * g.C + c;
+      t[0] = v[0];
+      t[g.C] = v[1];
+      t[2 * g.C] = v[2];
+      t[3 * g.C] = 0.f;
+      t[4 * g.C] = 0.f;
+    }
+  }
+  __syncthreads();
+  // dx = rs*gamma*dzn - rs*(s1 + xh*s2)/n  =  dzn*da + x*db + dc     (coef rows 0..2 are rewritten in place: each
+  // channel is read and written by the same thread, and the per-thread copies xa/xc/gam/bet are already in registers)
+  const float inv_n = 1.f / (static_cast<float>(g.cpg) * g.HW);
+  for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
+    const int gi = c / g.cpg;
+    float s1 = 0.f, s2 = 0.f;
+    for (int k = gi * g.cpg; k < (gi + 1) * g.cpg; ++k) {
+      s1 += sAB[k];
+      s2 += sAB[g.C + k];
+    }
+    s1 *= inv_n;
+    s2 *= inv_n;
+    const float rs = coef[c], xcc = coef[g.C + c], gm = coef[2 * g.C + c];
+    if (s == 0 && p.dx_colsum) {  // sum_hw dx = rstd*(gamma*A - (HW*S1 + S2*Xh)/n), from the sample totals
+      const float* t = tot + static_cast<size_t>(b) * 5 * g.C + c;
+      p.dx_colsum[static_cast<size_t>(b) * g.C + c] = rs * (sAB[c] - (g.HW * s1 + s2 * t[2 * g.C]));
+    }
+    coef[c] = rs * gm;
+    coef[g.C + c] = -rs * s2 * rs;
+    coef[2 * g.C + c] = -rs * (s1 + s2 * xcc);
+  }
+  __syncthreads();
+  float da[CH8], db[CH8], dc[CH8];
+  ld8(coef + cv * CH8, da);
+  ld8(coef + g.C + cv * CH8, db);
+  ld8(coef + 2 * g.C + cv * CH8, dc);
+  bf16* dx = static_cast<bf16*>(p.dx) + gbase;
+  for (int r = lr; r < nrows; r += g.nlanes) {
+    const size_t off = static_cast<size_t>(r) * g.C + cv * CH8;
+    float f[CH8], d[CH8];
+    unpack8(*reinterpret_cast<const uint4*>(slab_x + off * 2), f);
+    unpack8(*reinterpret_cast<const uint4*>(slab_d + off * 2), d);
+#pragma unroll
+    for (int j = 0; j < CH8; ++j) d[j] = d[j] * da[j] + f[j] * db[j] + dc[j];
+    *reinterpret_cast<uint4*>(dx + off) = pack8(d);
+  }
+  if (g.S > 1) cluster_sync_all();  // no CTA may exit while a peer can still read its partials
+}
+
+// geometry of the slab path; returns false when the shape does not qualify (caller falls back to streaming)
+static bool make_slab_geom(int B, int HW, int C, int G, int nslabs, int nscratch, SlabGeom* g, int* threads,
+                           size_t* smem) {
+  if (C % CH8 || C % G || C / CH8 > 256) return false;
+  g->B = B; g->HW = HW; g->C = C; g->G = G; g->cpg = C / G; g->CV = C / CH8;
+  g->nlanes = 256 / g->CV;
+  if (g->nlanes > HW) g->nlanes = HW;
+  *threads = g->CV * g->nlanes;
+  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  const size_t budget = static_cast<size_t>(device_info().max_smem_optin) - 1024;
+  const int smax = getenv("PDDM_GN_S") ? atoi(getenv("PDDM_GN_S")) : 8;
+  for (int S = 8; S >= 1; S /= 2) {
+    const int rows = (HW + S - 1) / S;
+    // a CTA wants >= 4 rows per lane to amortise its fixed cost (barriers, folds, cluster exchange)
+    if (S > 1 && (S > smax || rows < 4 * g->nlanes || (S - 1) * rows >= HW || B * (S / 2) >= 8 * sms)) continue;
+    const int slab = (rows * C * 2 + 127) / 128 * 128;
+    const size_t need = static_cast<size_t>(nslabs) * slab +
+                        (static_cast<size_t>(nscratch) * g->nlanes * C + 9 * C + 4 * G) * sizeof(float) +
+                        kSlabChunks * sizeof(uint64_t);
+    if (need > budget) {
+      if (S == 8) return false;  // even the widest cluster does not fit
+      continue;
+    }
+    g->S = S;
+    g->rows_per_cta = rows;
+    g->slab_bytes = slab;
+    int cr = (rows + kSlabChunks - 1) / kSlabChunks;
+    cr = (cr + g->nlanes - 1) / g->nlanes * g->nlanes;
+    g->chunk_rows = cr;
+    *smem = need;
+    return true;
+  }
+  return false;
+}
+
 static int make_geom(int B, int HW, int C, int G, GnGeom* g, int* threads) {
   if (B <= 0 || HW <= 0 || C <= 0 || G <= 0) return PDDM_ERR_BAD_ARG;
   if (C % 8 || C % G || C / CH > 256) return PDDM_ERR_UNSUPPORTED;  // C <= 1024
@@ -411,6 +763,26 @@ extern "C" int pddm_gn_silu_fwd(const pddm_gn_fwd_params* p, void* workspace, si
   int rc = make_geom(p->B, p->HW, p->C, p->G, &g, &threads);
   if (rc) return rc;
   if (!aligned16(p->x) || !aligned16(p->y)) return PDDM_ERR_BAD_ARG;
+  if (!p->scale && p->x_dtype == PDDM_BF16 && !getenv("PDDM_GN_STREAM")) {
+    SlabGeom sg;
+    int st;
+    size_t ssm;
+    if (make_slab_geom(p->B, p->HW, p->C, p->G, 1, 2, &sg, &st, &ssm)) {
+      const void* fn = p->silu ? reinterpret_cast<const void*>(gn_fwd_slab_kernel<true>)
+                               : reinterpret_cast<const void*>(gn_fwd_slab_kernel<false>);
+      static bool attr_done[2] = {false, false};
+      if (!attr_done[p->silu ? 1 : 0]) {
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, device_info().max_smem_optin) !=
+            cudaSuccess)
+          return PDDM_ERR_CUDA;
+        attr_done[p->silu ? 1 : 0] = true;
+      }
+      pddm_gn_fwd_params pp = *p;
+      void* args[2] = {&pp, &sg};
+      rc = launch_cluster(fn, dim3(sg.S, sg.B), st, ssm, sg.S, s, args);
+      return rc ? rc : launch_status();
+    }
+  }
   const size_t smem = (2 * static_cast<size_t>(g.nlanes) * g.C + 4 * g.G) * sizeof(float);
   pddm_gn_fwd_params pp = *p;
   void* args[2] = {&pp, &g};
@@ -439,22 +811,47 @@ extern "C" int pddm_gn_silu_bwd(const pddm_gn_bwd_params* p, void* workspace, si
   if (workspace_bytes < need) return PDDM_ERR_WORKSPACE;
   float* tot = static_cast<float*>(workspace);
   const bool ss = p->scale != nullptr;
+  bool launched = false;
+  if (!ss && p->x_dtype == PDDM_BF16 && p->dx_dtype == PDDM_BF16 && !getenv("PDDM_GN_STREAM")) {
+    SlabGeom sg;
+    int st;
+    size_t ssm;
+    if (make_slab_geom(p->B, p->HW, p->C, p->G, 2, 3, &sg, &st, &ssm)) {
+      const void* fn = p->silu ? reinterpret_cast<const void*>(gn_bwd_slab_kernel<true>)
+                               : reinterpret_cast<const void*>(gn_bwd_slab_kernel<false>);
+      static bool attr_done[2] = {false, false};
+      if (!attr_done[p->silu ? 1 : 0]) {
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, device_info().max_smem_optin) !=
+            cudaSuccess)
+          return PDDM_ERR_CUDA;
+        attr_done[p->silu ? 1 : 0] = true;
+      }
+      pddm_gn_bwd_params pp = *p;
+      void* args[3] = {&pp, &tot, &sg};
+      rc = launch_cluster(fn, dim3(sg.S, sg.B), st, ssm, sg.S, s, args);
+      if (rc) return rc;
+      if (cudaPeekAtLastError() != cudaSuccess) return PDDM_ERR_CUDA;
+      launched = true;
+    }
+  }
   const int nq = ss ? 5 : 3;
   const size_t smem = (nq * static_cast<size_t>(g.nlanes) * g.C + 7 * g.C + 2 * g.G) * sizeof(float);
   const void* fn = p->silu ? (ss ? reinterpret_cast<const void*>(gn_bwd_cluster_kernel<true, true>)
                                  : reinterpret_cast<const void*>(gn_bwd_cluster_kernel<true, false>))
                            : (ss ? reinterpret_cast<const void*>(gn_bwd_cluster_kernel<false, true>)
                                  : reinterpret_cast<const void*>(gn_bwd_cluster_kernel<false, false>));
-  if (smem > 48 * 1024) {
+  if (!launched && smem > 48 * 1024) {
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
       return PDDM_ERR_UNSUPPORTED;
   }
-  pddm_gn_bwd_params pp = *p;
-  void* args[3] = {&pp, &tot, &g};
-  rc = launch_cluster(fn, dim3(g.S, g.B), threads, smem, g.S, s, args);
-  if (rc) return rc;
-  if (cudaPeekAtLastError() != cudaSuccess) return PDDM_ERR_CUDA;
-  if (p->dx_colsum || p->dshift || p->dscale) {
+  if (!launched) {
+    pddm_gn_bwd_params pp = *p;
+    void* args[3] = {&pp, &tot, &g};
+    rc = launch_cluster(fn, dim3(g.S, g.B), threads, smem, g.S, s, args);
+    if (rc) return rc;
+    if (cudaPeekAtLastError() != cudaSuccess) return PDDM_ERR_CUDA;
+  }
+  if (!launched && (p->dx_colsum || p->dshift || p->dscale)) {
     gn_bwd_per_sample_kernel<<<dim3((g.C + 127) / 128, g.B), 128, 0, s>>>(*p, tot, g);
     if (cudaPeekAtLastError() != cudaSuccess) return PDDM_ERR_CUDA;
   }
