@@ -355,6 +355,21 @@ typedef struct {
   const float* lr_dev;     /* if non-NULL overrides lr (LR schedulers under graph replay) */
 } pddm_adam_params;
 int pddm_adam_ema_step(const pddm_adam_params* p, pddm_stream_t stream);
+/* The same update over MANY separately allocated tensors in ONE launch (a model's parameter list as autograd
+ * leaves it: one gradient tensor per parameter).  descs: device array of pddm_adam_tensor; blocks: device array of
+ * int32 pairs (tensor index, first element) -- one thread block updates PDDM_ADAM_CHUNK consecutive elements of one
+ * tensor.  The scalar fields of hyper (lr ... lr_dev) apply to every tensor; its pointer fields and n are ignored. */
+#define PDDM_ADAM_CHUNK 8192
+typedef struct {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  float* ema; /* may be NULL */
+  int64_t n;
+} pddm_adam_tensor;
+int pddm_adam_ema_multi(const void* descs, const void* blocks, int32_t nblocks, const pddm_adam_params* hyper,
+                        pddm_stream_t stream);
 /* *counter += delta (single thread); advances device-side step counters between graph replays. */
 int pddm_counter_add(int32_t* counter, int32_t delta, pddm_stream_t stream);
 

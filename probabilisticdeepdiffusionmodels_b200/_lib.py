@@ -144,6 +144,7 @@ SIGNATURES = {
     "pddm_attn_fwd": (c_i32, [P(AttnFwdParams), c_vp]),
     "pddm_attn_bwd": (c_i32, [P(AttnBwdParams), c_vp]),
     "pddm_adam_ema_step": (c_i32, [P(AdamParams), c_vp]),
+    "pddm_adam_ema_multi": (c_i32, [c_vp, c_vp, c_i32, P(AdamParams), c_vp]),
     "pddm_counter_add": (c_i32, [c_vp, c_i32, c_vp]),
 }
 

@@ -130,6 +130,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
+  pdl_launch_dependents();  // after the TMEM allocation (see conv_fwd.cu)
+  pdl_wait();
   const uint32_t sQ = smem_u32(smem + a.off_q), sK = smem_u32(smem + a.off_k), sV = smem_u32(smem + a.off_v);
   const uint32_t sP = smem_u32(smem + a.off_p);
 
@@ -230,6 +232,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
+  pdl_launch_dependents();  // after the TMEM allocation (see conv_fwd.cu)
+  pdl_wait();
   const uint32_t sQ = smem_u32(smem + a.off_q), sDO = smem_u32(smem + a.off_do), sK = smem_u32(smem + a.off_k),
                  sV = smem_u32(smem + a.off_v), sP = smem_u32(smem + a.off_p);
   const uint32_t trow = tmem + (static_cast<uint32_t>(tid) << 16);
@@ -415,7 +419,7 @@ extern "C" int pddm_attn_fwd(const pddm_attn_fwd_params* p, pddm_stream_t s_) {
   if (cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            device_info().max_smem_optin) != cudaSuccess)
     return PDDM_ERR_CUDA;
-  attn_fwd_kernel<<<a.B * a.heads * a.nqt, 128, smem, s>>>(tmQ, tmKV, a);
+  PdlLaunch(a.B * a.heads * a.nqt, 128, smem, s)(attn_fwd_kernel, tmQ, tmKV, a);
   return launch_status();
 }
 
@@ -461,13 +465,13 @@ extern "C" int pddm_attn_bwd(const pddm_attn_bwd_params* p, pddm_stream_t s_) {
     return PDDM_ERR_CUDA;
   if (!two_pass) {
     a.pass = 0;
-    attn_bwd_kernel<<<a.B * a.heads, 128, smem, s>>>(tmQ, tmKV, tmDO, a);
+    PdlLaunch(a.B * a.heads, 128, smem, s)(attn_bwd_kernel, tmQ, tmKV, tmDO, a);
   } else {
     a.pass = 1;
-    attn_bwd_kernel<<<a.B * a.heads, 128, smem, s>>>(tmQ, tmKV, tmDO, a);
+    PdlLaunch(a.B * a.heads, 128, smem, s)(attn_bwd_kernel, tmQ, tmKV, tmDO, a);
     if (cudaPeekAtLastError() != cudaSuccess) return PDDM_ERR_CUDA;
     a.pass = 2;
-    attn_bwd_kernel<<<a.B * a.heads, 128, smem, s>>>(tmQ, tmKV, tmDO, a);
+    PdlLaunch(a.B * a.heads, 128, smem, s)(attn_bwd_kernel, tmQ, tmKV, tmDO, a);
   }
   return launch_status();
 }

@@ -86,6 +86,10 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // PDL: barriers, TMEM and the tensor-map prefetch were set up under the previous kernel's tail.  The trigger
+  // comes after our TMEM allocation so a dependent CTA can never take tensor memory this grid still needs.
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp >= 1 && warp <= 3) {
     // ---------------------------------------------------------------- TMA producers (3 single-lane issuers)
@@ -96,7 +100,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // lane: inside a divergent `if (lane == 0)` region the compiler wraps every UTMALDG / SYNCS operand in a
     // uniform-register waterfall loop (~100-200 cycles per instruction).
     const int pid = warp - 1;
-    const int kpt = a.kblocks_per_tap, ntaps = a.ntaps, bk = a.bk, block_n = a.block_n;
+    const int kpt = a.kblocks_per_tap, bk = a.bk, block_n = a.block_n;
     const int tiles_w = a.tiles_w, tiles_h = a.tiles_h, BW = a.BW, BH = a.BH, BB = a.BB;
     const uint32_t tx_bytes = ((dbg & 2) ? 0 : mt * a.a_tx_bytes) + ((dbg & 8) ? 0 : a.b_bytes);
     const uint32_t a_slot = a.a_slot_bytes;
@@ -480,6 +484,6 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
   }
   const int total_tiles = ((a.m_tiles + a.mt - 1) / a.mt) * a.n_tiles;
   const int grid = total_tiles < device_info().sm_count ? total_tiles : device_info().sm_count;
-  conv_fwd_kernel<<<grid, kConvThreads, smem_bytes, stream>>>(tmA, tmB, a);
+  PdlLaunch(grid, kConvThreads, smem_bytes, stream)(conv_fwd_kernel, tmA, tmB, a);
   return launch_status();
 }

@@ -72,6 +72,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // PDL: barriers, TMEM and the tensor-map prefetch were set up under the previous kernel's tail.  The trigger
+  // comes after our TMEM allocation so a dependent CTA can never take tensor memory this grid still needs.
+  pdl_launch_dependents();
+  pdl_wait();
 
   // item -> (split, n_tile, m_tile, tap): consecutive CTAs share the dY tile (same m_tile/split) across taps
   auto decode = [&](int item, int& tap, int& m_tile, int& n_tile, int& split) {
@@ -219,13 +223,21 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
 // dw[layout] (+)= sum_s partial[s][n][tap][c]   (fixed summation order: deterministic; 4 channels per thread)
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int Cout,
                                     int ntaps, int Cin, int layout, int accumulate) {
+  pdl_entry();
   const size_t total4 = static_cast<size_t>(Cout) * ntaps * Cin / 4;
   for (size_t i4 = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i4 < total4;
        i4 += static_cast<size_t>(gridDim.x) * blockDim.x) {
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k = 0; k < splits; ++k) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(partial) + k * total4 + i4);
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    // eight independent loads in flight, then the adds in split order (1x1 layers have up to ~150 splits and only
+    // a few thousand outputs: a dependent load-add chain would cost splits x DRAM latency)
+    for (int k0 = 0; k0 < splits; k0 += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (k0 + u < splits) v[u] = __ldg(reinterpret_cast<const float4*>(partial) + (k0 + u) * total4 + i4);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (k0 + u < splits) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
     }
     const size_t i = i4 * 4;
     if (layout == 0) {
@@ -356,13 +368,13 @@ extern "C" int pddm_conv2d_wgrad(const pddm_wgrad_params* p, void* workspace, si
       return PDDM_ERR_CUDA;
     attr_set = true;
   }
-  conv_wgrad_kernel<<<plan.grid, kWgThreads, plan.smem_bytes, stream>>>(tmDY, tmX, plan.a);
+  PdlLaunch(plan.grid, kWgThreads, plan.smem_bytes, stream)(conv_wgrad_kernel, tmDY, tmX, plan.a);
   if (cudaPeekAtLastError() != cudaSuccess) return PDDM_ERR_CUDA;
   const size_t total = static_cast<size_t>(p->Cout) * p->ntaps * p->Cin;
   int blocks = static_cast<int>((total / 4 + 255) / 256);
   if (blocks > 2368) blocks = 2368;
   if (blocks < 1) blocks = 1;
-  wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(plan.a.partial, p->dw, plan.a.splits, p->Cout, p->ntaps, p->Cin,
+  PdlLaunch(blocks, 256, 0, stream)(wgrad_reduce_kernel, plan.a.partial, p->dw, plan.a.splits, p->Cout, p->ntaps, p->Cin,
                                                   p->dw_layout, p->accumulate);
   return launch_status();
 }

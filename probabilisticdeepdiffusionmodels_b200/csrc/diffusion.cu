@@ -31,6 +31,7 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
 // src/engine.py:251-261: mean = x*a[t-1]; std = s[t-1]; x_t = mean + noise*std
 template <int VEC>
 __global__ void q_sample_kernel(pddm_q_sample_params p) {
+  pdl_entry();
   const int per = p.chw / VEC;
   const long long total = static_cast<long long>(p.B) * per;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -56,6 +57,7 @@ __global__ void q_sample_kernel(pddm_q_sample_params p) {
 // ------------------------------------------------------------------------------------------ squared error
 // one block per sample: L_b = mean_{c<C,hw} (noise - pred)^2 ; optional gradient wrt pred
 __global__ void sq_err_kernel(pddm_sq_err_params p) {
+  pdl_entry();
   __shared__ float sh[32];
   const int b = blockIdx.x;
   const int n = p.C * p.hw;
@@ -84,6 +86,7 @@ __global__ void sq_err_kernel(pddm_sq_err_params p) {
 //                         x_{t-1} = mean - sigma*z   (z skipped at t == 1)
 template <int VEC>
 __global__ void p_sample_kernel(pddm_p_sample_params p) {
+  pdl_entry();
   const int t = p.t_step_dev ? *p.t_step_dev : p.t_step;
   const int chw = p.C * p.hw;
   const int per = chw / VEC;
@@ -146,6 +149,7 @@ __global__ void p_sample_kernel(pddm_p_sample_params p) {
 }
 
 __global__ void step_advance_kernel(int32_t* t_dev, float* t_vec, int B) {
+  pdl_entry();
   // single block; every thread reads the old value before anyone writes the new one
   const int t_new = *t_dev - 1;
   __syncthreads();
@@ -191,6 +195,7 @@ __device__ __forceinline__ float normal_kl(float m1, float lv1, float m2, float 
 
 // one block per sample
 __global__ void vlb_kernel(pddm_vlb_params p) {
+  pdl_entry();
   __shared__ float sh[32];
   const int b = blockIdx.x;
   const int chw = p.C * p.hw;
@@ -251,6 +256,7 @@ __global__ void vlb_kernel(pddm_vlb_params p) {
 
 // ------------------------------------------------------------------------------------------ timestep embedding
 __global__ void temb_kernel(const void* t, int t_is_float, void* out, int out_dtype, int B, int dim, float neg_log_mp) {
+  pdl_entry();
   const int half = dim / 2;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * dim) return;
@@ -271,6 +277,7 @@ __global__ void temb_kernel(const void* t, int t_is_float, void* out, int out_dt
 // torch.optim.Adam semantics (no amsgrad): m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ;
 // p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps) ;  ema = d*ema + (1-d)*p
 __global__ void adam_kernel(pddm_adam_params p, float bc1, float bc2_sqrt) {
+  pdl_entry();
   const long long n4 = p.n / 4;
   if (p.step_dev) {
     const float st = static_cast<float>(*p.step_dev);
@@ -307,6 +314,68 @@ __global__ void adam_kernel(pddm_adam_params p, float bc1, float bc2_sqrt) {
   }
 }
 
+// multi-tensor variant: block -> (tensor, chunk) through a table; float4 path when all four arrays are 16 B aligned
+__global__ void __launch_bounds__(256) adam_multi_kernel(const pddm_adam_tensor* __restrict__ descs,
+                                                         const int2* __restrict__ blocks, pddm_adam_params p, float bc1,
+                                                         float bc2_sqrt) {
+  pdl_entry();
+  const int2 blk = blocks[blockIdx.x];
+  const pddm_adam_tensor d = descs[blk.x];
+  if (p.step_dev) {
+    const float st = static_cast<float>(*p.step_dev);
+    bc1 = 1.f - powf(p.beta1, st);
+    bc2_sqrt = sqrtf(1.f - powf(p.beta2, st));
+  }
+  const float step_size = (p.lr_dev ? *p.lr_dev : p.lr) / bc1;
+  const float b1 = p.beta1, b2 = p.beta2, wd = p.weight_decay, gs = p.grad_scale, eps = p.eps, ed = p.ema_decay;
+  const long long beg = blk.y;
+  const long long end = min(static_cast<long long>(d.n), beg + PDDM_ADAM_CHUNK);
+  auto upd = [&](float& w, float g, float& m, float& v) {
+    g *= gs;
+    if (wd != 0.f) g += wd * w;
+    m = b1 * m + (1.f - b1) * g;
+    v = b2 * v + (1.f - b2) * g * g;
+    w -= step_size * m / (sqrtf(v) / bc2_sqrt + eps);
+  };
+  const bool vec = ((reinterpret_cast<uintptr_t>(d.param) | reinterpret_cast<uintptr_t>(d.grad) |
+                     reinterpret_cast<uintptr_t>(d.exp_avg) | reinterpret_cast<uintptr_t>(d.exp_avg_sq) |
+                     reinterpret_cast<uintptr_t>(d.ema)) & 15) == 0;
+  long long i = beg;
+  if (vec) {
+    const long long end4 = beg + ((end - beg) & ~3LL);
+    for (i = beg + threadIdx.x * 4LL; i < end4; i += blockDim.x * 4LL) {
+      float4 w = *reinterpret_cast<float4*>(d.param + i);
+      const float4 g = *reinterpret_cast<const float4*>(d.grad + i);
+      float4 m = *reinterpret_cast<float4*>(d.exp_avg + i);
+      float4 v = *reinterpret_cast<float4*>(d.exp_avg_sq + i);
+      upd(w.x, g.x, m.x, v.x);
+      upd(w.y, g.y, m.y, v.y);
+      upd(w.z, g.z, m.z, v.z);
+      upd(w.w, g.w, m.w, v.w);
+      *reinterpret_cast<float4*>(d.param + i) = w;
+      *reinterpret_cast<float4*>(d.exp_avg + i) = m;
+      *reinterpret_cast<float4*>(d.exp_avg_sq + i) = v;
+      if (d.ema) {
+        float4 e = *reinterpret_cast<float4*>(d.ema + i);
+        e.x = ed * e.x + (1.f - ed) * w.x;
+        e.y = ed * e.y + (1.f - ed) * w.y;
+        e.z = ed * e.z + (1.f - ed) * w.z;
+        e.w = ed * e.w + (1.f - ed) * w.w;
+        *reinterpret_cast<float4*>(d.ema + i) = e;
+      }
+    }
+    i = end4;
+  }
+  for (long long k = i + threadIdx.x; k < end; k += blockDim.x) {  // unaligned tensors and the < 4 element tail
+    float w = d.param[k], m = d.exp_avg[k], v = d.exp_avg_sq[k];
+    upd(w, d.grad[k], m, v);
+    d.param[k] = w;
+    d.exp_avg[k] = m;
+    d.exp_avg_sq[k] = v;
+    if (d.ema) d.ema[k] = ed * d.ema[k] + (1.f - ed) * w;
+  }
+}
+
 static int ew_grid(long long work_items, int threads) {
   long long blocks = (work_items + threads - 1) / threads;
   const long long cap = static_cast<long long>(device_info().sm_count > 0 ? device_info().sm_count : 148) * 8;
@@ -326,8 +395,8 @@ extern "C" int pddm_q_sample(const pddm_q_sample_params* p, pddm_stream_t s_) {
     return PDDM_ERR_BAD_ARG;
   const bool v4 = p->chw % 4 == 0 && aligned16(p->x0) && aligned16(p->noise) && aligned16(p->x_t);
   const long long work = static_cast<long long>(p->B) * p->chw / (v4 ? 4 : 1);
-  if (v4) q_sample_kernel<4><<<ew_grid(work, 256), 256, 0, s>>>(*p);
-  else q_sample_kernel<1><<<ew_grid(work, 256), 256, 0, s>>>(*p);
+  if (v4) PdlLaunch(ew_grid(work, 256), 256, 0, s)(q_sample_kernel<4>, *p);
+  else PdlLaunch(ew_grid(work, 256), 256, 0, s)(q_sample_kernel<1>, *p);
   return launch_status();
 }
 
@@ -335,7 +404,7 @@ extern "C" int pddm_sq_err(const pddm_sq_err_params* p, pddm_stream_t s_) {
   cudaStream_t s = static_cast<cudaStream_t>(s_);
   if (!p || !p->pred || !p->noise || p->B <= 0 || p->C <= 0 || p->hw <= 0 || p->c_total < p->C) return PDDM_ERR_BAD_ARG;
   if (p->grad_pred && !p->gscale) return PDDM_ERR_BAD_ARG;
-  sq_err_kernel<<<p->B, 256, 0, s>>>(*p);
+  PdlLaunch(p->B, 256, 0, s)(sq_err_kernel, *p);
   return launch_status();
 }
 
@@ -350,14 +419,14 @@ extern "C" int pddm_p_sample_step(const pddm_p_sample_params* p, pddm_stream_t s
   const bool v4 = chw % 4 == 0 && (p->c_out * p->hw) % 4 == 0 && aligned16(p->x_t) && aligned16(p->model_out) &&
                   aligned16(p->x_prev) && (!p->z || aligned16(p->z));
   const long long work = static_cast<long long>(p->B) * chw / (v4 ? 4 : 1);
-  if (v4) p_sample_kernel<4><<<ew_grid(work, 256), 256, 0, s>>>(*p);
-  else p_sample_kernel<1><<<ew_grid(work, 256), 256, 0, s>>>(*p);
+  if (v4) PdlLaunch(ew_grid(work, 256), 256, 0, s)(p_sample_kernel<4>, *p);
+  else PdlLaunch(ew_grid(work, 256), 256, 0, s)(p_sample_kernel<1>, *p);
   return launch_status();
 }
 
 extern "C" int pddm_step_advance(int32_t* t_dev, float* t_vec, int32_t B, pddm_stream_t s_) {
   if (!t_dev || !t_vec || B <= 0) return PDDM_ERR_BAD_ARG;
-  step_advance_kernel<<<1, 256, 0, static_cast<cudaStream_t>(s_)>>>(t_dev, t_vec, B);
+  PdlLaunch(1, 256, 0, static_cast<cudaStream_t>(s_))(step_advance_kernel, t_dev, t_vec, B);
   return launch_status();
 }
 
@@ -366,7 +435,7 @@ extern "C" int pddm_vlb_terms(const pddm_vlb_params* p, pddm_stream_t s_) {
     return PDDM_ERR_BAD_ARG;
   if (p->mode != 2 && (!p->x_t || !p->model_out || !p->t)) return PDDM_ERR_BAD_ARG;
   if (p->mode == 1 && p->c_out != 2 * p->C) return PDDM_ERR_BAD_ARG;
-  vlb_kernel<<<p->B, 256, 0, static_cast<cudaStream_t>(s_)>>>(*p);
+  PdlLaunch(p->B, 256, 0, static_cast<cudaStream_t>(s_))(vlb_kernel, *p);
   return launch_status();
 }
 
@@ -375,15 +444,16 @@ extern "C" int pddm_timestep_embedding(const void* t, int32_t t_is_float, void* 
   if (!t || !out || B <= 0 || dim <= 0) return PDDM_ERR_BAD_ARG;
   const float neg_log_mp = -static_cast<float>(log(static_cast<double>(max_period)));
   const int n = B * dim;
-  temb_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(s_)>>>(t, t_is_float, out, out_dtype, B, dim,
+  PdlLaunch((n + 255) / 256, 256, 0, static_cast<cudaStream_t>(s_))(temb_kernel, t, t_is_float, out, out_dtype, B, dim,
                                                                           neg_log_mp);
   return launch_status();
 }
 
-__global__ void counter_add_kernel(int32_t* c, int32_t d) { *c += d; }
+__global__ void counter_add_kernel(int32_t* c, int32_t d) {
+  pdl_entry(); *c += d; }
 extern "C" int pddm_counter_add(int32_t* counter, int32_t delta, pddm_stream_t s_) {
   if (!counter) return PDDM_ERR_BAD_ARG;
-  counter_add_kernel<<<1, 1, 0, static_cast<cudaStream_t>(s_)>>>(counter, delta);
+  PdlLaunch(1, 1, 0, static_cast<cudaStream_t>(s_))(counter_add_kernel, counter, delta);
   return launch_status();
 }
 
@@ -393,6 +463,18 @@ extern "C" int pddm_adam_ema_step(const pddm_adam_params* p, pddm_stream_t s_) {
     return PDDM_ERR_BAD_ARG;
   const float bc1 = 1.f - static_cast<float>(pow(static_cast<double>(p->beta1), p->step));
   const float bc2 = 1.f - static_cast<float>(pow(static_cast<double>(p->beta2), p->step));
-  adam_kernel<<<ew_grid(p->n / 4, 256), 256, 0, static_cast<cudaStream_t>(s_)>>>(*p, bc1, sqrtf(bc2));
+  PdlLaunch(ew_grid(p->n / 4, 256), 256, 0, static_cast<cudaStream_t>(s_))(adam_kernel, *p, bc1, sqrtf(bc2));
+  return launch_status();
+}
+
+extern "C" int pddm_adam_ema_multi(const void* descs, const void* blocks, int32_t nblocks, const pddm_adam_params* p,
+                                   pddm_stream_t s_) {
+  if (!descs || !blocks || !p || nblocks <= 0 || p->step < 0) return PDDM_ERR_BAD_ARG;
+  if (!p->step_dev && p->step < 1) return PDDM_ERR_BAD_ARG;
+  const float bc1 = 1.f - static_cast<float>(pow(static_cast<double>(p->beta1), p->step));
+  const float bc2 = 1.f - static_cast<float>(pow(static_cast<double>(p->beta2), p->step));
+  PdlLaunch(nblocks, 256, 0, static_cast<cudaStream_t>(s_))(adam_multi_kernel,
+                                                             static_cast<const pddm_adam_tensor*>(descs),
+                                                             static_cast<const int2*>(blocks), *p, bc1, sqrtf(bc2));
   return launch_status();
 }

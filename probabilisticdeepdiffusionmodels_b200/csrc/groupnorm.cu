@@ -74,6 +74,7 @@ __device__ __forceinline__ float cluster_fold(const float* local_ptr, int S) {
 // ------------------------------------------------------------------------------------------------ forward
 template <bool SILU, bool SS>
 __global__ void __launch_bounds__(256, 4) gn_fwd_cluster_kernel(pddm_gn_fwd_params p, GnGeom g) {
+  pdl_entry();
   extern __shared__ float sh[];  // scratch[2][nlanes][C] | part[G][2] | stat[G][2]
   const int b = blockIdx.y, s = blockIdx.x;  // s = rank in the cluster
   const int cv = threadIdx.x % g.CV, lr = threadIdx.x / g.CV;
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(256, 4) gn_fwd_cluster_kernel(pddm_gn_fwd_para
 // Pass 1 parks dzn in the dx buffer (rounded to dx's dtype); pass 2 turns it into dx in place.
 template <bool SILU, bool SS>
 __global__ void __launch_bounds__(256, 3) gn_bwd_cluster_kernel(pddm_gn_bwd_params p, float* __restrict__ tot, GnGeom g) {
+  pdl_entry();
   extern __shared__ float sh[];  // scratch[NQ][nlanes][C] | part[5][C] | sA[C] sB[C] | S1[G] S2[G]
   constexpr int NQ = SS ? 5 : 3;
   const int b = blockIdx.y, s = blockIdx.x;
@@ -318,6 +320,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_cluster_kernel(pddm_gn_bwd_para
 
 // pass 3a (tiny): per-sample by-products from tot[b][5][C]; grid = (C/128, B)
 __global__ void gn_bwd_per_sample_kernel(pddm_gn_bwd_params p, const float* __restrict__ tot, GnGeom g) {
+  pdl_entry();
   const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
   if (c >= g.C) return;
   const int gi = c / g.cpg;
@@ -337,6 +340,7 @@ __global__ void gn_bwd_per_sample_kernel(pddm_gn_bwd_params p, const float* __re
 }
 // pass 3b (tiny): dgamma / dbeta = fixed-order sums over the batch; block = 32 channels x 32 batch lanes
 __global__ void gn_bwd_finalize_kernel(pddm_gn_bwd_params p, const float* __restrict__ tot, GnGeom g) {
+  pdl_entry();
   __shared__ float sg[32][33], sb[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x, bl = threadIdx.y;
   float dg = 0.f, db = 0.f;
@@ -424,6 +428,7 @@ __device__ __forceinline__ void ld8(const float* sm, float* r) {
 
 template <bool SILU>
 __global__ void __launch_bounds__(256, 2) gn_fwd_slab_kernel(pddm_gn_fwd_params p, SlabGeom g) {
+  pdl_entry();
   extern __shared__ __align__(128) uint8_t smraw[];
   uint8_t* slab = smraw;
   float* scratch = reinterpret_cast<float*>(smraw + g.slab_bytes);  // [2][nlanes][C]
@@ -530,6 +535,7 @@ __global__ void __launch_bounds__(256, 2) gn_fwd_slab_kernel(pddm_gn_fwd_params 
 template <bool SILU>
 __global__ void __launch_bounds__(256, 2)
 gn_bwd_slab_kernel(pddm_gn_bwd_params p, float* __restrict__ tot, SlabGeom g) {
+  pdl_entry();
   extern __shared__ __align__(128) uint8_t smraw[];
   uint8_t* slab_x = smraw;
   uint8_t* slab_d = smraw + g.slab_bytes;
@@ -720,20 +726,8 @@ static int make_geom(int B, int HW, int C, int G, GnGeom* g, int* threads) {
 }
 
 static int launch_cluster(const void* func, dim3 grid, int threads, size_t smem, int S, cudaStream_t s, void** args) {
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = grid;
-  cfg.blockDim = dim3(threads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = S;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelExC(&cfg, func, args) == cudaSuccess ? PDDM_OK : PDDM_ERR_CUDA;
+  PdlLaunch l(grid, dim3(threads), smem, s, S);
+  return l.launch_c(func, args) == cudaSuccess ? PDDM_OK : PDDM_ERR_CUDA;
 }
 
 }  // namespace pddm
@@ -852,9 +846,9 @@ extern "C" int pddm_gn_silu_bwd(const pddm_gn_bwd_params* p, void* workspace, si
     if (cudaPeekAtLastError() != cudaSuccess) return PDDM_ERR_CUDA;
   }
   if (!launched && (p->dx_colsum || p->dshift || p->dscale)) {
-    gn_bwd_per_sample_kernel<<<dim3((g.C + 127) / 128, g.B), 128, 0, s>>>(*p, tot, g);
+    PdlLaunch(dim3((g.C + 127) / 128, g.B), 128, 0, s)(gn_bwd_per_sample_kernel, *p, tot, g);
     if (cudaPeekAtLastError() != cudaSuccess) return PDDM_ERR_CUDA;
   }
-  gn_bwd_finalize_kernel<<<(g.C + 31) / 32, dim3(32, 32), 0, s>>>(*p, tot, g);
+  PdlLaunch((g.C + 31) / 32, dim3(32, 32), 0, s)(gn_bwd_finalize_kernel, *p, tot, g);
   return launch_status();
 }

@@ -1,8 +1,19 @@
+#include <stdlib.h>
 #include "host_common.h"
 
 #include <mutex>
 
 namespace pddm {
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PDDM_PDL");
+    v = (e && e[0] == '1') ? 1 : 0;  // opt-in: measured neutral inside CUDA graphs (17.0 vs 16.8 ms/step)
+  }
+  return v == 1;
+}
+
 
 const DeviceInfo& device_info() {
   // Per-process, per-current-device cache (one process per GPU is the deployment model).

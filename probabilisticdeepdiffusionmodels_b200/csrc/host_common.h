@@ -29,4 +29,57 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t*
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------
+// Every kernel of this library starts with griddepcontrol.launch_dependents (the next kernel in the stream may
+// be scheduled as soon as all of OUR CTAs have started) and executes griddepcontrol.wait before its first global
+// memory access (blocks until every kernel it depends on has completed and flushed).  Launched with the
+// programmatic-stream-serialization attribute, the launch latency and prologue (barrier init, TMEM allocation,
+// tensor-map prefetch) of kernel N+1 overlap the tail of kernel N -- ~1200 launches per training step.
+// Opt-in with PDDM_PDL=1: inside replayed CUDA graphs (the product path) it measured neutral, so the default
+// launches without the attribute, which turns both instructions into no-ops.
+bool pdl_enabled();
+
+struct PdlLaunch {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[2];
+  PdlLaunch(dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x = 0) {
+    cfg = cudaLaunchConfig_t();
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    int n = 0;
+    if (cluster_x > 0) {
+      attr[n].id = cudaLaunchAttributeClusterDimension;
+      attr[n].val.clusterDim.x = cluster_x;
+      attr[n].val.clusterDim.y = 1;
+      attr[n].val.clusterDim.z = 1;
+      ++n;
+    }
+    if (pdl_enabled()) {
+      attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[n].val.programmaticStreamSerializationAllowed = 1;
+      ++n;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n;
+  }
+#ifdef __CUDACC__
+  template <typename... KArgs, typename... Args>
+  cudaError_t operator()(void (*kernel)(KArgs...), Args&&... args) {
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<Args&&>(args)...);
+  }
+#endif
+  cudaError_t launch_c(const void* fn, void** args) { return cudaLaunchKernelExC(&cfg, fn, args); }
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_entry() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+#endif
+
 }  // namespace pddm

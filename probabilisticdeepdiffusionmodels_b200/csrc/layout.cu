@@ -39,6 +39,7 @@ static int grid_for(long long items, int threads) {
 // ---------------------------------------------------------------------------------- NCHW <-> NHWC
 template <typename TOut>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, TOut* __restrict__ dst, int C, int HW) {
+  pdl_entry();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -56,6 +57,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, TOut* __restr
 }
 template <typename TIn>
 __global__ void nhwc_to_nchw_kernel(const TIn* __restrict__ src, float* __restrict__ dst, int C, int HW) {
+  pdl_entry();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -75,6 +77,7 @@ __global__ void nhwc_to_nchw_kernel(const TIn* __restrict__ src, float* __restri
 // ---------------------------------------------------------------------------------- channel copy / add
 __global__ void copy_channels_kernel(const bf16* __restrict__ src, int ld_src, bf16* __restrict__ dst, int ld_dst,
                                      long long M, int C8) {
+  pdl_entry();
   const long long n = M * C8;
   GRID_STRIDE(i, n) {
     const long long m = i / C8;
@@ -84,6 +87,7 @@ __global__ void copy_channels_kernel(const bf16* __restrict__ src, int ld_src, b
 }
 __global__ void add_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ y,
                                 long long n8) {
+  pdl_entry();
   GRID_STRIDE(i, n8) {
     float fa[8], fb[8];
     unpack8(a[i], fa);
@@ -96,6 +100,7 @@ __global__ void add_bf16_kernel(const uint4* __restrict__ a, const uint4* __rest
 
 // ---------------------------------------------------------------------------------- upsample / phases
 __global__ void upsample2x_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int B, int H, int W, int C8) {
+  pdl_entry();
   const long long n = static_cast<long long>(B) * 2 * H * 2 * W * C8;
   GRID_STRIDE(i, n) {
     const int c = static_cast<int>(i % C8);
@@ -109,6 +114,7 @@ __global__ void upsample2x_kernel(const bf16* __restrict__ src, bf16* __restrict
 }
 __global__ void upsample2x_bwd_kernel(const bf16* __restrict__ gd, bf16* __restrict__ gs, int B, int H, int W,
                                       int C8) {
+  pdl_entry();
   const long long n = static_cast<long long>(B) * H * W * C8;
   GRID_STRIDE(i, n) {
     const int c = static_cast<int>(i % C8);
@@ -133,6 +139,7 @@ __global__ void upsample2x_bwd_kernel(const bf16* __restrict__ gd, bf16* __restr
 // split: dst[p][b][i][j] = src[b][2i + (p>>1)][2j + (p&1)] ; merge is the inverse (iterate over the full-res side)
 template <bool SPLIT>
 __global__ void phase_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int B, int H, int W, int C8) {
+  pdl_entry();
   const int H2 = H / 2, W2 = W / 2;
   const long long n = static_cast<long long>(B) * H * W * C8;
   GRID_STRIDE(i, n) {  // i indexes the full-resolution tensor
@@ -150,6 +157,7 @@ __global__ void phase_kernel(const bf16* __restrict__ src, bf16* __restrict__ ds
 
 // ---------------------------------------------------------------------------------- SiLU on vectors
 __global__ void silu_kernel(const float* __restrict__ x, void* __restrict__ y, int y_dtype, long long n) {
+  pdl_entry();
   GRID_STRIDE(i, n) {
     const float v = x[i];
     const float s = v / (1.f + expf(-v));
@@ -159,6 +167,7 @@ __global__ void silu_kernel(const float* __restrict__ x, void* __restrict__ y, i
 }
 __global__ void silu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx,
                                 long long n) {
+  pdl_entry();
   GRID_STRIDE(i, n) {
     const float v = x[i];
     const float sg = 1.f / (1.f + expf(-v));
@@ -169,6 +178,7 @@ __global__ void silu_bwd_kernel(const float* __restrict__ x, const float* __rest
 // ---------------------------------------------------------------------------------- dtype conversion
 template <typename TI, typename TO>
 __global__ void convert_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long n) {
+  pdl_entry();
   GRID_STRIDE(i, n) y[i] = static_cast<TO>(static_cast<float>(x[i]));
 }
 
@@ -177,6 +187,7 @@ __global__ void convert_kernel(const TI* __restrict__ x, TO* __restrict__ y, lon
 // (per-sample sums).  Partial results are combined with fp32 atomics into a zeroed / accumulated output.
 __global__ void colsum_kernel(const bf16* __restrict__ x, int ld, long long rows_per_seg, int C8, float* __restrict__ out,
                               int out_ld) {
+  pdl_entry();
   extern __shared__ float sh[];  // [C8*8]
   const int seg = blockIdx.y;
   const bf16* xs = x + static_cast<size_t>(seg) * rows_per_seg * ld;
@@ -212,6 +223,7 @@ __global__ void colsum_kernel(const bf16* __restrict__ x, int ld, long long rows
 // ---------------------------------------------------------------------------------- weight packing
 __global__ void pack_w_kernel(const float* __restrict__ w, bf16* __restrict__ dst, int Cout, int Cin, int ntaps,
                               int mode, int Cout_p, int Cin_p) {
+  pdl_entry();
   const long long n = static_cast<long long>(Cout_p) * Cin_p * ntaps;
   GRID_STRIDE(i, n) {  // i indexes dst (padded); padding rows / columns are written as zeros
     int co, ci, tap;
@@ -237,6 +249,7 @@ struct PackDesc {
 };
 constexpr int kPackChunk = 4096;
 __global__ void pack_multi_kernel(const PackDesc* __restrict__ descs, const int2* __restrict__ blocks) {
+  pdl_entry();
   const int2 blk = blocks[blockIdx.x];
   const PackDesc d = descs[blk.x];
   const long long n = static_cast<long long>(d.Cout_p) * d.Cin_p * d.ntaps;
@@ -258,6 +271,7 @@ __global__ void pack_multi_kernel(const PackDesc* __restrict__ descs, const int2
 }
 // out[c] = sum_m x[m, c] for a small fp32 matrix (fixed order); block = 32 columns x 8 row lanes
 __global__ void colsum_f32_kernel(const float* __restrict__ x, int M, int C, float* __restrict__ out) {
+  pdl_entry();
   __shared__ float sh[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x, rl = threadIdx.y;
   float a = 0.f;
@@ -278,6 +292,7 @@ __global__ void colsum_f32_kernel(const float* __restrict__ x, int M, int C, flo
 // out[b,h,w, ci*9 + tap] = x[b,ci,h+dh,w+dw]  (NCHW fp32 -> [B,H,W,Kp] bf16, zero outside the image and for k >= Cin*9)
 __global__ void im2col3x3_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B, int Cin, int H, int W,
                                  int Kp) {
+  pdl_entry();
   const int K8 = Kp / 8;
   const long long n = static_cast<long long>(B) * H * W * K8;
   GRID_STRIDE(i, n) {
@@ -302,6 +317,7 @@ __global__ void im2col3x3_kernel(const float* __restrict__ x, bf16* __restrict__
 // NCHW fp32 [B,C,HW] -> NHWC bf16 [B,HW,Cp] with channels >= C zero (Cp % 8 == 0)
 __global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int B, int C, int HW,
                                         int Cp) {
+  pdl_entry();
   const int C8 = Cp / 8;
   const long long n = static_cast<long long>(B) * HW * C8;
   GRID_STRIDE(i, n) {
@@ -320,6 +336,7 @@ __global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ src, bf16* __r
 // first C channels of NHWC fp32 [B,HW,ld] -> NCHW fp32 [B,C,HW]
 __global__ void nhwc_slice_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, int HW,
                                           int ld) {
+  pdl_entry();
   const long long n = static_cast<long long>(B) * C * HW;
   GRID_STRIDE(i, n) {
     const int pix = static_cast<int>(i % HW);
@@ -338,16 +355,16 @@ extern "C" int pddm_nchw_to_nhwc(const float* src, void* dst, int32_t dst_dtype,
                                  pddm_stream_t s) {
   if (!src || !dst || B <= 0 || C <= 0 || HW <= 0) return PDDM_ERR_BAD_ARG;
   dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
-  if (dst_dtype == PDDM_BF16) nchw_to_nhwc_kernel<bf16><<<grid, block, 0, S(s)>>>(src, static_cast<bf16*>(dst), C, HW);
-  else nchw_to_nhwc_kernel<float><<<grid, block, 0, S(s)>>>(src, static_cast<float*>(dst), C, HW);
+  if (dst_dtype == PDDM_BF16) PdlLaunch(grid, block, 0, S(s))(nchw_to_nhwc_kernel<bf16>, src, static_cast<bf16*>(dst), C, HW);
+  else PdlLaunch(grid, block, 0, S(s))(nchw_to_nhwc_kernel<float>, src, static_cast<float*>(dst), C, HW);
   return launch_status();
 }
 extern "C" int pddm_nhwc_to_nchw(const void* src, int32_t src_dtype, float* dst, int32_t B, int32_t C, int32_t HW,
                                  pddm_stream_t s) {
   if (!src || !dst || B <= 0 || C <= 0 || HW <= 0) return PDDM_ERR_BAD_ARG;
   dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
-  if (src_dtype == PDDM_BF16) nhwc_to_nchw_kernel<bf16><<<grid, block, 0, S(s)>>>(static_cast<const bf16*>(src), dst, C, HW);
-  else nhwc_to_nchw_kernel<float><<<grid, block, 0, S(s)>>>(static_cast<const float*>(src), dst, C, HW);
+  if (src_dtype == PDDM_BF16) PdlLaunch(grid, block, 0, S(s))(nhwc_to_nchw_kernel<bf16>, static_cast<const bf16*>(src), dst, C, HW);
+  else PdlLaunch(grid, block, 0, S(s))(nhwc_to_nchw_kernel<float>, static_cast<const float*>(src), dst, C, HW);
   return launch_status();
 }
 extern "C" int pddm_copy_channels(const void* src, int32_t ld_src, int32_t src_off, void* dst, int32_t ld_dst,
@@ -355,21 +372,21 @@ extern "C" int pddm_copy_channels(const void* src, int32_t ld_src, int32_t src_o
   if (!src || !dst || M <= 0 || C <= 0) return PDDM_ERR_BAD_ARG;
   if (C % 8 || ld_src % 8 || ld_dst % 8 || src_off % 8 || dst_off % 8 || !aligned16(src) || !aligned16(dst))
     return PDDM_ERR_UNSUPPORTED;
-  copy_channels_kernel<<<grid_for(M * (C / 8), 256), 256, 0, S(s)>>>(static_cast<const bf16*>(src) + src_off, ld_src,
+  PdlLaunch(grid_for(M * (C / 8), 256), 256, 0, S(s))(copy_channels_kernel, static_cast<const bf16*>(src) + src_off, ld_src,
                                                                       static_cast<bf16*>(dst) + dst_off, ld_dst, M, C / 8);
   return launch_status();
 }
 extern "C" int pddm_add_bf16(const void* a, const void* b, void* y, int64_t n, pddm_stream_t s) {
   if (!a || !b || !y || n <= 0) return PDDM_ERR_BAD_ARG;
   if (n % 8 || !aligned16(a) || !aligned16(b) || !aligned16(y)) return PDDM_ERR_UNSUPPORTED;
-  add_bf16_kernel<<<grid_for(n / 8, 256), 256, 0, S(s)>>>(static_cast<const uint4*>(a), static_cast<const uint4*>(b),
+  PdlLaunch(grid_for(n / 8, 256), 256, 0, S(s))(add_bf16_kernel, static_cast<const uint4*>(a), static_cast<const uint4*>(b),
                                                           static_cast<uint4*>(y), n / 8);
   return launch_status();
 }
 extern "C" int pddm_upsample2x(const void* src, void* dst, int32_t B, int32_t H, int32_t W, int32_t C, pddm_stream_t s) {
   if (!src || !dst || B <= 0 || H <= 0 || W <= 0 || C <= 0) return PDDM_ERR_BAD_ARG;
   if (C % 8) return PDDM_ERR_UNSUPPORTED;
-  upsample2x_kernel<<<grid_for(static_cast<long long>(B) * 4 * H * W * (C / 8), 256), 256, 0, S(s)>>>(
+  PdlLaunch(grid_for(static_cast<long long>(B) * 4 * H * W * (C / 8), 256), 256, 0, S(s))(upsample2x_kernel, 
       static_cast<const bf16*>(src), static_cast<bf16*>(dst), B, H, W, C / 8);
   return launch_status();
 }
@@ -377,21 +394,21 @@ extern "C" int pddm_upsample2x_bwd(const void* gd, void* gs, int32_t B, int32_t 
                                    pddm_stream_t s) {
   if (!gd || !gs || B <= 0 || H <= 0 || W <= 0 || C <= 0) return PDDM_ERR_BAD_ARG;
   if (C % 8) return PDDM_ERR_UNSUPPORTED;
-  upsample2x_bwd_kernel<<<grid_for(static_cast<long long>(B) * H * W * (C / 8), 256), 256, 0, S(s)>>>(
+  PdlLaunch(grid_for(static_cast<long long>(B) * H * W * (C / 8), 256), 256, 0, S(s))(upsample2x_bwd_kernel, 
       static_cast<const bf16*>(gd), static_cast<bf16*>(gs), B, H, W, C / 8);
   return launch_status();
 }
 extern "C" int pddm_phase_split(const void* src, void* dst, int32_t B, int32_t H, int32_t W, int32_t C, pddm_stream_t s) {
   if (!src || !dst || B <= 0 || H <= 0 || W <= 0 || C <= 0) return PDDM_ERR_BAD_ARG;
   if (C % 8 || H % 2 || W % 2) return PDDM_ERR_UNSUPPORTED;
-  phase_kernel<true><<<grid_for(static_cast<long long>(B) * H * W * (C / 8), 256), 256, 0, S(s)>>>(
+  PdlLaunch(grid_for(static_cast<long long>(B) * H * W * (C / 8), 256), 256, 0, S(s))(phase_kernel<true>, 
       static_cast<const bf16*>(src), static_cast<bf16*>(dst), B, H, W, C / 8);
   return launch_status();
 }
 extern "C" int pddm_phase_merge(const void* src, void* dst, int32_t B, int32_t H, int32_t W, int32_t C, pddm_stream_t s) {
   if (!src || !dst || B <= 0 || H <= 0 || W <= 0 || C <= 0) return PDDM_ERR_BAD_ARG;
   if (C % 8 || H % 2 || W % 2) return PDDM_ERR_UNSUPPORTED;
-  phase_kernel<false><<<grid_for(static_cast<long long>(B) * H * W * (C / 8), 256), 256, 0, S(s)>>>(
+  PdlLaunch(grid_for(static_cast<long long>(B) * H * W * (C / 8), 256), 256, 0, S(s))(phase_kernel<false>, 
       static_cast<const bf16*>(src), static_cast<bf16*>(dst), B, H, W, C / 8);
   return launch_status();
 }
@@ -399,21 +416,21 @@ extern "C" int pddm_convert(const void* x, int32_t x_dtype, void* y, int32_t y_d
   if (!x || !y || n <= 0) return PDDM_ERR_BAD_ARG;
   const int g = grid_for(n, 256);
   if (x_dtype == PDDM_F32 && y_dtype == PDDM_BF16)
-    convert_kernel<float, bf16><<<g, 256, 0, S(s)>>>(static_cast<const float*>(x), static_cast<bf16*>(y), n);
+    PdlLaunch(g, 256, 0, S(s))(convert_kernel<float, bf16>, static_cast<const float*>(x), static_cast<bf16*>(y), n);
   else if (x_dtype == PDDM_BF16 && y_dtype == PDDM_F32)
-    convert_kernel<bf16, float><<<g, 256, 0, S(s)>>>(static_cast<const bf16*>(x), static_cast<float*>(y), n);
+    PdlLaunch(g, 256, 0, S(s))(convert_kernel<bf16, float>, static_cast<const bf16*>(x), static_cast<float*>(y), n);
   else
     return PDDM_ERR_UNSUPPORTED;
   return launch_status();
 }
 extern "C" int pddm_silu(const float* x, void* y, int32_t y_dtype, int64_t n, pddm_stream_t s) {
   if (!x || !y || n <= 0) return PDDM_ERR_BAD_ARG;
-  silu_kernel<<<grid_for(n, 256), 256, 0, S(s)>>>(x, y, y_dtype, n);
+  PdlLaunch(grid_for(n, 256), 256, 0, S(s))(silu_kernel, x, y, y_dtype, n);
   return launch_status();
 }
 extern "C" int pddm_silu_bwd(const float* x, const float* dy, float* dx, int64_t n, pddm_stream_t s) {
   if (!x || !dy || !dx || n <= 0) return PDDM_ERR_BAD_ARG;
-  silu_bwd_kernel<<<grid_for(n, 256), 256, 0, S(s)>>>(x, dy, dx, n);
+  PdlLaunch(grid_for(n, 256), 256, 0, S(s))(silu_bwd_kernel, x, dy, dx, n);
   return launch_status();
 }
 
@@ -438,7 +455,7 @@ static int colsum_launch(const void* x, int ld, long long rows_per_seg, int segs
     }
   }
   dim3 grid(static_cast<unsigned>(gx), segs);
-  colsum_kernel<<<grid, threads, C * sizeof(float), s>>>(static_cast<const bf16*>(x), ld, rows_per_seg, C8, out, out_ld);
+  PdlLaunch(grid, threads, C * sizeof(float), s)(colsum_kernel, static_cast<const bf16*>(x), ld, rows_per_seg, C8, out, out_ld);
   return launch_status();
 }
 extern "C" int pddm_colsum(const void* x, int32_t ld, int64_t M, int32_t C, float* out, int32_t accumulate,
@@ -460,25 +477,25 @@ extern "C" int pddm_pack_conv_weight(const float* w, void* dst, int32_t Cout, in
                                      int32_t Cout_pad, int32_t Cin_pad, pddm_stream_t s) {
   if (!w || !dst || Cout <= 0 || Cin <= 0 || ntaps <= 0 || mode < 0 || mode > 1 || Cout_pad < Cout || Cin_pad < Cin)
     return PDDM_ERR_BAD_ARG;
-  pack_w_kernel<<<grid_for(static_cast<long long>(Cout_pad) * Cin_pad * ntaps, 256), 256, 0, S(s)>>>(
+  PdlLaunch(grid_for(static_cast<long long>(Cout_pad) * Cin_pad * ntaps, 256), 256, 0, S(s))(pack_w_kernel, 
       w, static_cast<bf16*>(dst), Cout, Cin, ntaps, mode, Cout_pad, Cin_pad);
   return launch_status();
 }
 extern "C" int pddm_pack_weights_multi(const void* descs, const void* blocks, int32_t nblocks, pddm_stream_t s) {
   if (!descs || !blocks || nblocks <= 0) return PDDM_ERR_BAD_ARG;
-  pack_multi_kernel<<<nblocks, 256, 0, S(s)>>>(static_cast<const PackDesc*>(descs), static_cast<const int2*>(blocks));
+  PdlLaunch(nblocks, 256, 0, S(s))(pack_multi_kernel, static_cast<const PackDesc*>(descs), static_cast<const int2*>(blocks));
   return launch_status();
 }
 extern "C" int pddm_colsum_f32(const float* x, int32_t M, int32_t C, float* out, pddm_stream_t s) {
   if (!x || !out || M <= 0 || C <= 0) return PDDM_ERR_BAD_ARG;
-  colsum_f32_kernel<<<(C + 31) / 32, dim3(32, 8), 0, S(s)>>>(x, M, C, out);
+  PdlLaunch((C + 31) / 32, dim3(32, 8), 0, S(s))(colsum_f32_kernel, x, M, C, out);
   return launch_status();
 }
 extern "C" int pddm_im2col3x3(const float* x_nchw, void* out, int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t Kp,
                               pddm_stream_t s) {
   if (!x_nchw || !out || B <= 0 || Cin <= 0 || H <= 0 || W <= 0) return PDDM_ERR_BAD_ARG;
   if (Kp % 8 || Kp < Cin * 9) return PDDM_ERR_UNSUPPORTED;
-  im2col3x3_kernel<<<grid_for(static_cast<long long>(B) * H * W * (Kp / 8), 256), 256, 0, S(s)>>>(
+  PdlLaunch(grid_for(static_cast<long long>(B) * H * W * (Kp / 8), 256), 256, 0, S(s))(im2col3x3_kernel, 
       x_nchw, static_cast<bf16*>(out), B, Cin, H, W, Kp);
   return launch_status();
 }
@@ -486,13 +503,13 @@ extern "C" int pddm_nchw_to_nhwc_padded(const float* src, void* dst, int32_t B, 
                                         pddm_stream_t s) {
   if (!src || !dst || B <= 0 || C <= 0 || HW <= 0) return PDDM_ERR_BAD_ARG;
   if (Cp % 8 || Cp < C) return PDDM_ERR_UNSUPPORTED;
-  nchw_to_nhwc_pad_kernel<<<grid_for(static_cast<long long>(B) * HW * (Cp / 8), 256), 256, 0, S(s)>>>(
+  PdlLaunch(grid_for(static_cast<long long>(B) * HW * (Cp / 8), 256), 256, 0, S(s))(nchw_to_nhwc_pad_kernel, 
       src, static_cast<bf16*>(dst), B, C, HW, Cp);
   return launch_status();
 }
 extern "C" int pddm_nhwc_slice_to_nchw(const float* src, float* dst, int32_t B, int32_t C, int32_t HW, int32_t ld,
                                        pddm_stream_t s) {
   if (!src || !dst || B <= 0 || C <= 0 || HW <= 0 || ld < C) return PDDM_ERR_BAD_ARG;
-  nhwc_slice_to_nchw_kernel<<<grid_for(static_cast<long long>(B) * C * HW, 256), 256, 0, S(s)>>>(src, dst, B, C, HW, ld);
+  PdlLaunch(grid_for(static_cast<long long>(B) * C * HW, 256), 256, 0, S(s))(nhwc_slice_to_nchw_kernel, src, dst, B, C, HW, ld);
   return launch_status();
 }

@@ -19,6 +19,8 @@ from contextlib import contextmanager
 from typing import List, Tuple
 
 import numpy as np
+import os
+
 import torch
 
 from . import functional as F
@@ -515,8 +517,16 @@ class Engine(_Base):
         optional ``grad_hook`` (e.g. the data-parallel all-reduce), Adam, EMA) as a CUDA graph.
         Returns ``step(x) -> loss`` replaying it on a static input buffer."""
         dev = self.device
-        if optimizer is None:
+        fused_ema = False
+        if optimizer is None and os.environ.get("PDDM_TORCH_ADAM") == "1":  # A/B switch: torch's fused Adam
             optimizer = torch.optim.Adam(self.model.parameters(), capturable=True, fused=True, **self.optimizer_config)
+        if optimizer is None:
+            # Adam and (when configured) the EMA of the weights in one launch over the parameter list
+            from .optim import FusedAdam
+            fused_ema = self.ema is not None and not any(True for _ in self.model.buffers())
+            optimizer = FusedAdam(self.model.parameters(), **self.optimizer_config,
+                                  ema_params=self.ema.module.parameters() if fused_ema else None,
+                                  ema_decay=self.ema.decay if fused_ema else None)
         st = {"x": torch.zeros(batch_shape, dtype=torch.float32, device=dev), "opt": optimizer}
         params = [p for p in self.model.parameters() if p.requires_grad]
 
@@ -540,7 +550,7 @@ class Engine(_Base):
             if grad_hook is not None:
                 grad_hook(params)
             optimizer.step()
-            if self.ema is not None:
+            if self.ema is not None and not fused_ema:
                 self.ema.update(self.model)
             return loss.detach(), per.detach(), t
 
@@ -561,6 +571,8 @@ class Engine(_Base):
         k0 = _lib.KERNELS[0]
         with torch.cuda.graph(graph):
             st["loss"], st["per"], st["t"] = body()
+        if hasattr(optimizer, "flush_tables"):
+            optimizer.flush_tables()  # pointer tables recorded during capture (gradient addresses of the graph pool)
         st["kernels_per_step"] = _lib.KERNELS[0] - k0  # kernels of this library captured in one step
         st["graph"] = graph
         self._train_graph = st

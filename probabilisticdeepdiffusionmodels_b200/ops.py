@@ -245,6 +245,7 @@ def _(dy, xin, weight, stride, upsample, in_h, in_w, need_dx, need_dbias, need_d
 def _conv_setup(ctx, inputs, output):
     x, weight, bias, bcast, residual, stride, upsample = inputs
     _, aux = output
+    ctx.set_materialize_grads(False)  # no zero-filled gradient tensors for the auxiliary outputs
     ctx.save_for_backward(x if aux.numel() == 0 else aux, weight)
     ctx.meta = (stride, upsample, x.shape[1], x.shape[2])
     ctx.needs = (x.requires_grad, bias is not None and bias.requires_grad, bcast is not None and bcast.requires_grad,
@@ -434,6 +435,7 @@ def _(x, dy, gamma, beta, scale, shift, mean, rstd, groups, silu):
 def _gn_setup(ctx, inputs, output):
     x, gamma, beta, scale, shift, groups, eps, silu = inputs
     _, mean, rstd = output
+    ctx.set_materialize_grads(False)
     ctx.save_for_backward(x, gamma, beta, mean, rstd, *([scale, shift] if scale is not None else []))
     ctx.meta = (groups, silu, scale is not None)
 
@@ -478,6 +480,7 @@ def _(qkv, out, dout, lse, heads):
 
 
 def _attn_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)
     ctx.save_for_backward(inputs[0], output[0], output[1])
     ctx.heads = inputs[1]
 
@@ -561,8 +564,12 @@ def _stem_backward(ctx, dy, _dp):
     return None, dw, db  # the model input needs no gradient (x_t is data)
 
 
-torch.library.register_autograd("pddm::stem_conv", _stem_backward,
-                                setup_context=lambda ctx, inputs, output: ctx.save_for_backward(output[1], inputs[1]))
+def _stem_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)
+    ctx.save_for_backward(output[1], inputs[1])
+
+
+torch.library.register_autograd("pddm::stem_conv", _stem_backward, setup_context=_stem_setup)
 
 
 @torch.library.custom_op("pddm::head_conv", mutates_args=())
@@ -659,6 +666,7 @@ class HybridLoss(torch.autograd.Function):
         per, _ = F.sq_err(model_out, noise)
         vb, gv = F.vlb_terms(x0, x_t, model_out, t, tabs, mode=1, want_grad_v=True)
         ctx.save_for_backward(model_out, noise, gv)
+        ctx.set_materialize_grads(False)
         ctx.vb_weight = vb_weight
         return per + vb_weight * vb, vb
 
