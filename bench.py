@@ -313,7 +313,19 @@ def main():
                     "chain_steps_timed": args.sample_steps, "chain_seconds": chain_s, "batch_per_gpu": B,
                     "finite": bool(torch.isfinite(out).all())}
 
+    def finish():
+        # Multi-rank teardown: leave without running the NCCL communicator destructors.  Both
+        # dist.destroy_process_group() and a plain interpreter exit were observed to hang here once the captured
+        # step (NCCL all-reduce node + side-stream weight-gradient branch) had been replayed; every collective of
+        # the run has completed by now (max-over-ranks reductions above), so nothing is lost.
+        if world > 1:
+            torch.cuda.synchronize(dev)
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+
     if rank != 0:
+        finish()
         return
     burst, sustained, hbm, src = peaks()
     fwd = fwd_flops_per_image(arch, RES)
@@ -338,9 +350,8 @@ def main():
         r = cpu_reference_arm(2, 1)
         line["cpu_baseline"] = {"value": r["train_img_s"], "unit": "img/s", "cores": r["cores"], "kind": "port",
                                 "sample": r["sample"], "samples_per_s": r["samples_s"]}
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+    finish()
 
 
 if __name__ == "__main__":
