@@ -175,10 +175,15 @@ int pddm_convert(const void* x, int32_t x_dtype, void* y, int32_t y_dtype, int64
 /* SiLU on an fp32 vector -> out dtype; and its backward (dx = dy * silu'(x)).  (src/modules/nn.py:13-15) */
 int pddm_silu(const float* x, void* y, int32_t y_dtype, int64_t n, pddm_stream_t stream);
 int pddm_silu_bwd(const float* x, const float* dy, float* dx, int64_t n, pddm_stream_t stream);
-/* out[c] (+)= sum_m x[m, c]  (x bf16 [M, ld], fp32 out [C]); used for conv bias gradients. */
-int pddm_colsum(const void* x, int32_t ld, int64_t M, int32_t C, float* out, int32_t accumulate, pddm_stream_t stream);
+/* Column sums, deterministic (two-stage, fixed summation order; no atomics).  workspace: pddm_colsum_workspace bytes
+ * for (rows per segment, segments, C) -- (M, 1, C) for pddm_colsum, (HW, B, C) for the per-sample variant.
+ * out[c] (+)= sum_m x[m, c]  (x bf16 [M, ld], fp32 out [C]); used for conv bias gradients. */
+size_t pddm_colsum_workspace(int64_t rows_per_segment, int32_t segments, int32_t C);
+int pddm_colsum(const void* x, int32_t ld, int64_t M, int32_t C, float* out, int32_t accumulate, void* workspace,
+                size_t workspace_bytes, pddm_stream_t stream);
 /* out[b, c] = sum_{hw} x[b, hw, c] : per-sample column sums (gradient of the broadcast emb add). */
-int pddm_colsum_per_sample(const void* x, int32_t B, int32_t HW, int32_t C, float* out, pddm_stream_t stream);
+int pddm_colsum_per_sample(const void* x, int32_t B, int32_t HW, int32_t C, float* out, void* workspace,
+                           size_t workspace_bytes, pddm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * GroupNorm(32 groups, eps) [+ per-sample scale/shift] [+ SiLU]   (src/modules/nn.py:13-20,94-101;

@@ -126,8 +126,9 @@ SIGNATURES = {
     "pddm_convert": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i64, c_vp]),
     "pddm_silu": (c_i32, [c_vp, c_vp, c_i32, c_i64, c_vp]),
     "pddm_silu_bwd": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp]),
-    "pddm_colsum": (c_i32, [c_vp, c_i32, c_i64, c_i32, c_vp, c_i32, c_vp]),
-    "pddm_colsum_per_sample": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "pddm_colsum_workspace": (C.c_size_t, [c_i64, c_i32, c_i32]),
+    "pddm_colsum": (c_i32, [c_vp, c_i32, c_i64, c_i32, c_vp, c_i32, c_vp, C.c_size_t, c_vp]),
+    "pddm_colsum_per_sample": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, C.c_size_t, c_vp]),
     "pddm_gn_silu_fwd_workspace": (c_sz, [c_i32, c_i32]),
     "pddm_gn_silu_fwd": (c_i32, [P(GnFwdParams), c_vp, c_sz, c_vp]),
     "pddm_gn_silu_bwd_workspace": (c_sz, [c_i32, c_i32]),
@@ -210,7 +211,8 @@ def dt(t):
 LAUNCHES = [0]  # number of C-ABI compute calls issued from Python
 KERNELS = [0]   # number of kernels those calls launched (bench.py's gpu_launches claim is derived from it)
 # entry points that launch more than one kernel (memsets are not counted)
-_KERNELS_PER_CALL = {"pddm_gn_silu_fwd": 1, "pddm_gn_silu_bwd": 3, "pddm_conv2d_wgrad": 2}
+_KERNELS_PER_CALL = {"pddm_gn_silu_fwd": 1, "pddm_gn_silu_bwd": 2, "pddm_conv2d_wgrad": 2, "pddm_colsum": 2,
+                     "pddm_colsum_per_sample": 2}
 
 
 def call(name, *args):

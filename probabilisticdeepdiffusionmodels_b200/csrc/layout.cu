@@ -183,41 +183,66 @@ __global__ void convert_kernel(const TI* __restrict__ x, TO* __restrict__ y, lon
 }
 
 // ---------------------------------------------------------------------------------- column sums
-// blockDim = (C8 vectors, rows lanes); each block reduces a slab of rows; grid.y = independent row segments
-// (per-sample sums).  Partial results are combined with fp32 atomics into a zeroed / accumulated output.
-__global__ void colsum_kernel(const bf16* __restrict__ x, int ld, long long rows_per_seg, int C8, float* __restrict__ out,
-                              int out_ld) {
+// Deterministic two-stage reduction (no atomics): stage 1, grid (gx, segs): a block of C/8 vector columns x nlanes
+// row lanes sums its slab of rows, folds the lanes through shared memory in lane order and writes one partial row;
+// stage 2 folds the gx partial rows of each segment in index order.  grid.y = independent row segments (per-sample
+// sums).  With gx == 1 stage 1 writes the result directly.
+__global__ void colsum_partial_kernel(const bf16* __restrict__ x, int ld, long long rows_per_seg, long long rows_per_blk,
+                                      int C8, float* __restrict__ part, float* __restrict__ out, int out_ld,
+                                      int accumulate) {
   pdl_entry();
-  extern __shared__ float sh[];  // [C8*8]
-  const int seg = blockIdx.y;
+  extern __shared__ float sh[];  // [nlanes][C]
+  const int seg = blockIdx.y, C = C8 * 8;
   const bf16* xs = x + static_cast<size_t>(seg) * rows_per_seg * ld;
   const int cv = threadIdx.x % C8, lane_r = threadIdx.x / C8, nlanes = blockDim.x / C8;
+  const long long r0 = blockIdx.x * rows_per_blk, r1 = min(rows_per_seg, r0 + rows_per_blk);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (lane_r < nlanes) {
-    const long long stride = static_cast<long long>(gridDim.x) * nlanes;
-    for (long long r = static_cast<long long>(blockIdx.x) * nlanes + lane_r; r < rows_per_seg; r += 4 * stride) {
-      uint4 v[4];
+  for (long long r = r0 + lane_r; r < r1; r += 4LL * nlanes) {
+    uint4 v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (r + u * stride < rows_per_seg) v[u] = *reinterpret_cast<const uint4*>(xs + (r + u * stride) * ld + cv * 8);
+    for (int u = 0; u < 4; ++u)
+      if (r + u * nlanes < r1) v[u] = *reinterpret_cast<const uint4*>(xs + (r + u * nlanes) * ld + cv * 8);
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (r + u * stride < rows_per_seg) {
-          float f[8];
-          unpack8(v[u], f);
+    for (int u = 0; u < 4; ++u)
+      if (r + u * nlanes < r1) {
+        float f[8];
+        unpack8(v[u], f);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] += f[j];
-        }
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
+  }
+  float* d = sh + lane_r * C + cv * 8;
+  *reinterpret_cast<float4*>(d) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  *reinterpret_cast<float4*>(d + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float v = 0.f;
+    for (int l = 0; l < nlanes; ++l) v += sh[l * C + c];
+    if (gridDim.x == 1) {
+      float* o = out + static_cast<size_t>(seg) * out_ld + c;
+      *o = accumulate ? *o + v : v;
+    } else {
+      part[(static_cast<size_t>(seg) * gridDim.x + blockIdx.x) * C + c] = v;
     }
   }
-  for (int i = threadIdx.x; i < C8 * 8; i += blockDim.x) sh[i] = 0.f;
+}
+// stage 2: out[seg][c] (+)= sum_k part[seg][k][c], k in index order; block = 32 columns x 8 partial lanes
+__global__ void colsum_fold_kernel(const float* __restrict__ part, int gx, int C, float* __restrict__ out, int out_ld,
+                                   int accumulate) {
+  pdl_entry();
+  __shared__ float sh[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x, ly = threadIdx.y, seg = blockIdx.y;
+  float a = 0.f;
+  if (c < C)
+    for (int k = ly; k < gx; k += 8) a += part[(static_cast<size_t>(seg) * gx + k) * C + c];
+  sh[ly][threadIdx.x] = a;
   __syncthreads();
-  if (lane_r < nlanes) {
+  if (ly == 0 && c < C) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&sh[cv * 8 + j], acc[j]);
+    for (int k = 1; k < 8; ++k) a += sh[k][threadIdx.x];
+    float* o = out + static_cast<size_t>(seg) * out_ld + c;
+    *o = accumulate ? *o + a : a;
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < C8 * 8; i += blockDim.x) atomicAdd(&out[static_cast<size_t>(seg) * out_ld + i], sh[i]);
 }
 
 // ---------------------------------------------------------------------------------- weight packing
@@ -434,44 +459,77 @@ extern "C" int pddm_silu_bwd(const float* x, const float* dy, float* dx, int64_t
   return launch_status();
 }
 
-static int colsum_launch(const void* x, int ld, long long rows_per_seg, int segs, int C, float* out, int out_ld,
-                         int accumulate, cudaStream_t s) {
-  if (C % 8 || ld % 8 || !aligned16(x) || C > 8192) return PDDM_ERR_UNSUPPORTED;
-  const int C8 = C / 8;
-  int threads = C8 * (256 / C8 > 0 ? 256 / C8 : 1);
-  if (threads > 1024) return PDDM_ERR_UNSUPPORTED;
-  const int nlanes = threads / C8;
-  long long gx = (rows_per_seg + static_cast<long long>(nlanes) * 16 - 1) / (static_cast<long long>(nlanes) * 16);
-  const long long cap = 2LL * 148 / (segs < 296 ? segs : 296) + 1;
-  if (gx > cap) gx = cap;
+struct ColsumGeom {
+  int C8, threads, nlanes, gx;
+  long long rows_per_blk;
+};
+static int colsum_geom(long long rows_per_seg, int segs, int C, ColsumGeom* g) {
+  if (C % 8 || C > 8192 || C <= 0 || rows_per_seg <= 0 || segs <= 0) return PDDM_ERR_UNSUPPORTED;
+  g->C8 = C / 8;
+  g->nlanes = 256 / g->C8 > 0 ? 256 / g->C8 : 1;
+  g->threads = g->C8 * g->nlanes;
+  if (g->threads > 1024) return PDDM_ERR_UNSUPPORTED;
+  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  long long gx = (4LL * sms + segs - 1) / segs;                                  // ~4 blocks per SM overall
+  const long long max_gx = (rows_per_seg + 4LL * g->nlanes - 1) / (4LL * g->nlanes);  // >= 4 rows per lane
+  if (gx > max_gx) gx = max_gx;
   if (gx < 1) gx = 1;
-  if (!accumulate) {
-    if (out_ld == C) {
-      if (cudaMemsetAsync(out, 0, static_cast<size_t>(segs) * C * sizeof(float), s) != cudaSuccess) return PDDM_ERR_CUDA;
-    } else {
-      for (int i = 0; i < segs; ++i)
-        if (cudaMemsetAsync(out + static_cast<size_t>(i) * out_ld, 0, C * sizeof(float), s) != cudaSuccess)
-          return PDDM_ERR_CUDA;
+  g->rows_per_blk = (rows_per_seg + gx - 1) / gx;
+  g->gx = static_cast<int>((rows_per_seg + g->rows_per_blk - 1) / g->rows_per_blk);
+  return PDDM_OK;
+}
+static size_t colsum_ws_bytes(long long rows_per_seg, int segs, int C) {
+  ColsumGeom g;
+  const int cw = C > 4096 ? 4096 : C;  // wide matrices are reduced in column panels that reuse the workspace
+  if (colsum_geom(rows_per_seg, segs, cw, &g) != PDDM_OK) return 0;
+  return g.gx > 1 ? static_cast<size_t>(segs) * g.gx * cw * sizeof(float) : 16;
+}
+static int colsum_launch(const void* x, int ld, long long rows_per_seg, int segs, int C, float* out, int out_ld,
+                         int accumulate, void* ws, size_t ws_bytes, cudaStream_t s) {
+  if (ld % 8 || !aligned16(x)) return PDDM_ERR_UNSUPPORTED;
+  ColsumGeom g;
+  int rc = colsum_geom(rows_per_seg, segs, C, &g);
+  if (rc) return rc;
+  const size_t smem = static_cast<size_t>(g.nlanes) * C * sizeof(float);
+  if (g.gx > 1 && (!ws || ws_bytes < static_cast<size_t>(segs) * g.gx * C * sizeof(float))) return PDDM_ERR_WORKSPACE;
+  if (smem > 48 * 1024) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      if (cudaFuncSetAttribute(colsum_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) !=
+          cudaSuccess)
+        return PDDM_ERR_CUDA;
+      attr_set = true;
     }
+    if (smem > 64 * 1024) return PDDM_ERR_UNSUPPORTED;
   }
-  dim3 grid(static_cast<unsigned>(gx), segs);
-  PdlLaunch(grid, threads, C * sizeof(float), s)(colsum_kernel, static_cast<const bf16*>(x), ld, rows_per_seg, C8, out, out_ld);
+  PdlLaunch(dim3(g.gx, segs), g.threads, smem, s)(colsum_partial_kernel, static_cast<const bf16*>(x), ld, rows_per_seg,
+                                                   g.rows_per_blk, g.C8, static_cast<float*>(ws), out, out_ld,
+                                                   accumulate);
+  if (cudaPeekAtLastError() != cudaSuccess) return PDDM_ERR_CUDA;
+  if (g.gx > 1)
+    PdlLaunch(dim3((C + 31) / 32, segs), dim3(32, 8), 0, s)(colsum_fold_kernel, static_cast<const float*>(ws), g.gx, C,
+                                                            out, out_ld, accumulate);
   return launch_status();
 }
+extern "C" size_t pddm_colsum_workspace(int64_t rows_per_segment, int32_t segments, int32_t C) {
+  return colsum_ws_bytes(rows_per_segment, segments, C);
+}
 extern "C" int pddm_colsum(const void* x, int32_t ld, int64_t M, int32_t C, float* out, int32_t accumulate,
-                           pddm_stream_t s) {
+                           void* workspace, size_t workspace_bytes, pddm_stream_t s) {
   if (!x || !out || M <= 0 || C <= 0) return PDDM_ERR_BAD_ARG;
   // wide matrices (e.g. the batched timestep-embedding projection) are reduced in column panels
   for (int c0 = 0; c0 < C; c0 += 4096) {
     const int cw = C - c0 < 4096 ? C - c0 : 4096;
-    int rc = colsum_launch(static_cast<const bf16*>(x) + c0, ld, M, 1, cw, out + c0, cw, accumulate, S(s));
+    int rc = colsum_launch(static_cast<const bf16*>(x) + c0, ld, M, 1, cw, out + c0, cw, accumulate, workspace,
+                           workspace_bytes, S(s));
     if (rc) return rc;
   }
   return PDDM_OK;
 }
-extern "C" int pddm_colsum_per_sample(const void* x, int32_t B, int32_t HW, int32_t C, float* out, pddm_stream_t s) {
+extern "C" int pddm_colsum_per_sample(const void* x, int32_t B, int32_t HW, int32_t C, float* out, void* workspace,
+                                      size_t workspace_bytes, pddm_stream_t s) {
   if (!x || !out || B <= 0 || HW <= 0 || C <= 0) return PDDM_ERR_BAD_ARG;
-  return colsum_launch(x, C, HW, B, C, out, C, 0, S(s));
+  return colsum_launch(x, C, HW, B, C, out, C, 0, workspace, workspace_bytes, S(s));
 }
 extern "C" int pddm_pack_conv_weight(const float* w, void* dst, int32_t Cout, int32_t Cin, int32_t ntaps, int32_t mode,
                                      int32_t Cout_pad, int32_t Cin_pad, pddm_stream_t s) {

@@ -149,7 +149,9 @@ def colsum(x2d_bf16, C_):
     _chk(x2d_bf16, bf16)
     out = torch.empty(C_, dtype=f32, device=x2d_bf16.device)
     M = x2d_bf16.numel() // x2d_bf16.shape[-1]
-    L.call("pddm_colsum", L.ptr(x2d_bf16), x2d_bf16.shape[-1], C.c_int64(M), C_, L.ptr(out), 0, L.stream())
+    ws = _ws(L.load().pddm_colsum_workspace(C.c_int64(M), 1, C_), x2d_bf16.device)
+    L.call("pddm_colsum", L.ptr(x2d_bf16), x2d_bf16.shape[-1], C.c_int64(M), C_, L.ptr(out), 0, L.ptr(ws),
+           C.c_size_t(ws.numel()), L.stream())
     return out
 
 
@@ -166,7 +168,9 @@ def colsum_per_sample(x):
     _chk(x, bf16)
     B, C_ = x.shape[0], x.shape[-1]
     out = torch.empty((B, C_), dtype=f32, device=x.device)
-    L.call("pddm_colsum_per_sample", L.ptr(x), B, x.numel() // (B * C_), C_, L.ptr(out), L.stream())
+    HW = x.numel() // (B * C_)
+    ws = _ws(L.load().pddm_colsum_workspace(C.c_int64(HW), B, C_), x.device)
+    L.call("pddm_colsum_per_sample", L.ptr(x), B, HW, C_, L.ptr(out), L.ptr(ws), C.c_size_t(ws.numel()), L.stream())
     return out
 
 

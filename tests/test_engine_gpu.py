@@ -165,3 +165,21 @@ def test_nll_eval_batched_over_t_matches_sequential(monkeypatch):
         bat, _ = eng._calculate_L_intermediate(x0, 11)
     assert len(seq) == len(bat) == 11
     torch.testing.assert_close(torch.stack(bat), torch.stack(seq), rtol=2e-3, atol=1e-5)
+
+
+def test_captured_train_step_is_bitwise_reproducible():
+    """No atomics anywhere on the training path (split-K reduce, GroupNorm, column sums, attention backward all sum
+    in a fixed order): two runs from the same seed end with bit-identical parameters."""
+    def run():
+        torch.manual_seed(1234)
+        torch.cuda.manual_seed(1234)
+        eng = make_engine("cosine", log_loss_per_t=False)
+        x = (torch.arange(8 * 28 * 28, device="cuda").float().view(8, 1, 28, 28) % 97) / 48.0 - 1.0
+        step = eng.capture_train_step(tuple(x.shape))
+        losses = [float(step(x)) for _ in range(5)]
+        return losses, [p.detach().clone() for p in eng.model.parameters()]
+
+    la, pa = run()
+    lb, pb = run()
+    assert la == lb
+    assert all(torch.equal(a, b) for a, b in zip(pa, pb))

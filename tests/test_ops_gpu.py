@@ -282,3 +282,20 @@ def test_fused_adam_multi_matches_torch_adam_and_ema():
         opt_ref.step()
     for p, q in zip(ours, ref):
         torch.testing.assert_close(p, q, rtol=1e-5, atol=1e-6)
+
+
+def test_colsum_is_deterministic_and_handles_big_and_wide_shapes():
+    """Two-stage column sums (no atomics): bit-identical across runs; multi-block, per-sample and >4096-column panels."""
+    from probabilisticdeepdiffusionmodels_b200 import functional as F
+    big = rnd(128 * 1024, 128, seed=11).to(bf16).cuda()  # one 32x32 C=128 gradient tensor at B=128
+    a, b = F.colsum(big, 128), F.colsum(big, 128)
+    assert torch.equal(a, b)
+    assert rel(a, big.double().sum(0)) < 1e-5
+    ps = big.view(128, 1024, 128)
+    pa, pb = F.colsum_per_sample(ps), F.colsum_per_sample(ps)
+    assert torch.equal(pa, pb)
+    assert rel(pa, ps.double().sum(1)) < 1e-5
+    wide = rnd(64, 5120, seed=12).to(bf16).cuda()  # batched timestep-embedding projection width
+    assert rel(F.colsum(wide, 5120), wide.double().sum(0)) < 1e-5
+    odd = rnd(3, 7, 40, seed=13).to(bf16).cuda()  # ragged rows per block
+    assert rel(F.colsum_per_sample(odd), odd.double().sum(1)) < 1e-5
