@@ -296,15 +296,18 @@ int pddm_pack_conv_weight(const float* w, void* dst, int32_t Cout, int32_t Cin, 
                           int32_t Cout_pad, int32_t Cin_pad, pddm_stream_t stream);
 
 /* Re-pack every weight of a model in ONE launch (after each optimiser step).  descs: device array of
- * pddm_pack_desc; blocks: device array of int32 pairs (descriptor index, first destination element) -- one
- * thread block packs PDDM_PACK_CHUNK consecutive destination elements of one tensor. */
-#define PDDM_PACK_CHUNK 4096
+ * pddm_pack_desc; blocks: device array of int32 pairs (descriptor index, tile index) -- one thread block packs one
+ * tile of PDDM_PACK_TILE output channels x PDDM_PACK_TILE input channels x all taps of one tensor; tiles are numbered
+ * row-major over (ceil(Cout_pad/TILE), ceil(Cin_pad/TILE)).  Cout_pad and Cin_pad must be multiples of 8.
+ * max_ntaps: the largest ntaps among the descriptors (sizes the shared-memory tile). */
+#define PDDM_PACK_TILE 32
 typedef struct {
   const float* src;
   void* dst; /* bf16 */
   int32_t Cout, Cin, ntaps, mode, Cout_pad, Cin_pad;
 } pddm_pack_desc;
-int pddm_pack_weights_multi(const void* descs, const void* blocks, int32_t nblocks, pddm_stream_t stream);
+int pddm_pack_weights_multi(const void* descs, const void* blocks, int32_t nblocks, int32_t max_ntaps,
+                            pddm_stream_t stream);
 /* out[c] = sum_m x[m, c] for a small fp32 matrix [M, C] (deterministic). */
 int pddm_colsum_f32(const float* x, int32_t M, int32_t C, float* out, pddm_stream_t stream);
 

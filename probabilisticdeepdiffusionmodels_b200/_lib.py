@@ -84,7 +84,7 @@ class PackDesc(C.Structure):
                 ("Cout_pad", c_i32), ("Cin_pad", c_i32)]
 
 
-PACK_CHUNK = 4096
+PACK_TILE = 32  # PDDM_PACK_TILE
 
 
 class AttnFwdParams(C.Structure):
@@ -137,7 +137,7 @@ SIGNATURES = {
     "pddm_conv2d_wgrad_workspace": (c_sz, [P(WgradParams)]),
     "pddm_conv2d_wgrad": (c_i32, [P(WgradParams), c_vp, c_sz, c_vp]),
     "pddm_pack_conv_weight": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
-    "pddm_pack_weights_multi": (c_i32, [c_vp, c_vp, c_i32, c_vp]),
+    "pddm_pack_weights_multi": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp]),
     "pddm_colsum_f32": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp]),
     "pddm_im2col3x3": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "pddm_nchw_to_nhwc_padded": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),

@@ -266,32 +266,55 @@ __global__ void pack_w_kernel(const float* __restrict__ w, bf16* __restrict__ ds
   }
 }
 
-// all weights of a model in ONE launch: block i packs elements [chunk0, chunk0 + kPackChunk) of tensor blocks[i].x
+// all weights of a model in ONE launch: block i packs tile blocks[i].y of tensor blocks[i].x.  A tile is 32 output
+// channels x 32 input channels x all taps: the fp32 source rows are read coalesced into shared memory (for a fixed
+// output channel, 32 input channels x ntaps floats are contiguous), then gathered out of shared memory (odd strides:
+// conflict-free) into 16-byte bf16 stores in either pack order.  (The first version read the source with a stride of
+// ntaps floats and wrote single bf16 values: one LSU wavefront per element, 413 us per step for the CIFAR UNet.)
 struct PackDesc {
   const float* src;
   bf16* dst;
   int Cout, Cin, ntaps, mode, Cout_p, Cin_p;
 };
-constexpr int kPackChunk = 4096;
-__global__ void pack_multi_kernel(const PackDesc* __restrict__ descs, const int2* __restrict__ blocks) {
+constexpr int kPackTile = 32;
+__global__ void __launch_bounds__(256) pack_multi_kernel(const PackDesc* __restrict__ descs,
+                                                         const int2* __restrict__ blocks) {
   pdl_entry();
+  extern __shared__ float tile[];  // [32][32 * ntaps + 1]
   const int2 blk = blocks[blockIdx.x];
   const PackDesc d = descs[blk.x];
-  const long long n = static_cast<long long>(d.Cout_p) * d.Cin_p * d.ntaps;
-  const long long end = min(n, static_cast<long long>(blk.y) + kPackChunk);
-  for (long long i = blk.y + threadIdx.x; i < end; i += blockDim.x) {
-    int co, ci, tap;
-    if (d.mode == 0) {
-      ci = static_cast<int>(i % d.Cin_p);
-      tap = static_cast<int>((i / d.Cin_p) % d.ntaps);
-      co = static_cast<int>(i / (static_cast<long long>(d.Cin_p) * d.ntaps));
-    } else {
-      co = static_cast<int>(i % d.Cout_p);
-      tap = d.ntaps - 1 - static_cast<int>((i / d.Cout_p) % d.ntaps);
-      ci = static_cast<int>(i / (static_cast<long long>(d.Cout_p) * d.ntaps));
+  const int nt = d.ntaps;
+  const int n_ci_blk = (d.Cin_p + kPackTile - 1) / kPackTile;
+  const int co0 = (blk.y / n_ci_blk) * kPackTile, ci0 = (blk.y % n_ci_blk) * kPackTile;
+  const int row_len = kPackTile * nt, pitch = row_len + 1;
+  const int valid_len = max(0, min(kPackTile, d.Cin - ci0)) * nt;  // contiguous floats per source row
+  for (int idx = threadIdx.x; idx < kPackTile * row_len; idx += blockDim.x) {
+    const int r = idx / row_len, k = idx - r * row_len;
+    const int co = co0 + r;
+    tile[r * pitch + k] =
+        (co < d.Cout && k < valid_len) ? d.src[(static_cast<long long>(co) * d.Cin + ci0) * nt + k] : 0.f;
+  }
+  __syncthreads();
+  // work item = one 16-byte store: (row of the destination tile, tap, piece of 8 channels)
+  const int items = kPackTile * nt * (kPackTile / 8);
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int piece = it & 3, tap = (it >> 2) % nt, r = (it >> 2) / nt;
+    float v[8];
+    long long dst_off;
+    if (d.mode == 0) {  // dst[co][tap][ci]: r = output channel, piece = 8 input channels
+      const int co = co0 + r, ci = ci0 + piece * 8;
+      if (co >= d.Cout_p || ci >= d.Cin_p) continue;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = tile[r * pitch + (piece * 8 + j) * nt + tap];
+      dst_off = (static_cast<long long>(co) * nt + tap) * d.Cin_p + ci;
+    } else {  // dst[ci][ntaps-1-tap][co]: r = input channel, piece = 8 output channels
+      const int ci = ci0 + r, co = co0 + piece * 8;
+      if (ci >= d.Cin_p || co >= d.Cout_p) continue;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = tile[(piece * 8 + j) * pitch + r * nt + tap];
+      dst_off = (static_cast<long long>(ci) * nt + (nt - 1 - tap)) * d.Cout_p + co;
     }
-    const float v = (co < d.Cout && ci < d.Cin) ? d.src[(static_cast<long long>(co) * d.Cin + ci) * d.ntaps + tap] : 0.f;
-    d.dst[i] = __float2bfloat16(v);
+    *reinterpret_cast<uint4*>(d.dst + dst_off) = pack8(v);
   }
 }
 // out[c] = sum_m x[m, c] for a small fp32 matrix (fixed order); block = 32 columns x 8 row lanes
@@ -539,9 +562,21 @@ extern "C" int pddm_pack_conv_weight(const float* w, void* dst, int32_t Cout, in
       w, static_cast<bf16*>(dst), Cout, Cin, ntaps, mode, Cout_pad, Cin_pad);
   return launch_status();
 }
-extern "C" int pddm_pack_weights_multi(const void* descs, const void* blocks, int32_t nblocks, pddm_stream_t s) {
-  if (!descs || !blocks || nblocks <= 0) return PDDM_ERR_BAD_ARG;
-  PdlLaunch(nblocks, 256, 0, S(s))(pack_multi_kernel, static_cast<const PackDesc*>(descs), static_cast<const int2*>(blocks));
+extern "C" int pddm_pack_weights_multi(const void* descs, const void* blocks, int32_t nblocks, int32_t max_ntaps,
+                                       pddm_stream_t s) {
+  if (!descs || !blocks || nblocks <= 0 || max_ntaps <= 0 || max_ntaps > PDDM_MAX_TAPS) return PDDM_ERR_BAD_ARG;
+  const size_t smem = static_cast<size_t>(kPackTile) * (kPackTile * max_ntaps + 1) * sizeof(float);
+  if (smem > 48 * 1024) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      if (cudaFuncSetAttribute(pack_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess)
+        return PDDM_ERR_CUDA;
+      attr_set = true;
+    }
+    if (smem > 96 * 1024) return PDDM_ERR_UNSUPPORTED;
+  }
+  PdlLaunch(nblocks, 256, smem, S(s))(pack_multi_kernel, static_cast<const PackDesc*>(descs),
+                                       static_cast<const int2*>(blocks));
   return launch_status();
 }
 extern "C" int pddm_colsum_f32(const float* x, int32_t M, int32_t C, float* out, pddm_stream_t s) {

@@ -143,7 +143,9 @@ class WeightArena:
             d = descs[i]
             d.src, d.dst = w.data_ptr(), view.data_ptr()
             d.Cout, d.Cin, d.ntaps, d.mode, d.Cout_pad, d.Cin_pad = w.shape[0], w.shape[1], ntaps, mode, cop, cip
-            blocks += [(i, c0) for c0 in range(0, n, L.PACK_CHUNK)]
+            tiles = -(-cop // L.PACK_TILE) * -(-cip // L.PACK_TILE)
+            blocks += [(i, t) for t in range(tiles)]
+            self.max_ntaps = max(getattr(self, "max_ntaps", 1), ntaps)
         self._descs = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).to(device)
         self._blocks = torch.tensor(blocks, dtype=torch.int32).to(device)
         self.nblocks = len(blocks)
@@ -152,7 +154,8 @@ class WeightArena:
 
     def repack(self):
         from . import _lib as L
-        L.call("pddm_pack_weights_multi", L.ptr(self._descs), L.ptr(self._blocks), self.nblocks, L.stream())
+        L.call("pddm_pack_weights_multi", L.ptr(self._descs), L.ptr(self._blocks), self.nblocks, self.max_ntaps,
+               L.stream())
 
 
 def _empty(like):

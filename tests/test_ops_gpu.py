@@ -299,3 +299,32 @@ def test_colsum_is_deterministic_and_handles_big_and_wide_shapes():
     assert rel(F.colsum(wide, 5120), wide.double().sum(0)) < 1e-5
     odd = rnd(3, 7, 40, seed=13).to(bf16).cuda()  # ragged rows per block
     assert rel(F.colsum_per_sample(odd), odd.double().sum(1)) < 1e-5
+
+
+def test_weight_arena_multi_pack_equals_single_packs():
+    """ops.WeightArena (one tiled multi-tensor launch) reproduces pddm_pack_conv_weight bit for bit: 3x3 / 1x1 /
+    linear, both pack orders, ragged channel counts (tile edges) and zero padding."""
+    from probabilisticdeepdiffusionmodels_b200 import functional as F, ops
+    cases = [((128, 128, 3, 3), None, None), ((96, 40, 3, 3), None, None), ((256, 384, 1, 1), None, None),
+             ((8, 128, 3, 3), 32, None), ((6, 64, 3, 3), 8, 64), ((160, 96), None, None), ((33 * 8, 24, 3, 3), None, None)]
+    ws = [rnd(*shape, seed=40 + i).cuda() for i, (shape, _, _) in enumerate(cases)]
+    want = {}
+    for i, (w, (_, cop, cip)) in enumerate(zip(ws, cases)):
+        w3 = w if w.dim() > 2 else w.view(w.shape[0], w.shape[1], 1)
+        for mode in (0, 1):
+            want[(i, mode)] = F.pack_weight(w3, mode, cop, cip).clone()
+    arena = ops.WeightArena()
+    with arena.recording():
+        for i, (w, (_, cop, cip)) in enumerate(zip(ws, cases)):
+            w3 = w if w.dim() > 2 else w.view(w.shape[0], w.shape[1], 1)
+            for mode in (0, 1):
+                F.pack_weight(w3, mode, cop, cip)
+    arena.finalize(ws[0].device)
+    arena.repack()
+    with arena.active():
+        for i, (w, (_, cop, cip)) in enumerate(zip(ws, cases)):
+            w3 = w if w.dim() > 2 else w.view(w.shape[0], w.shape[1], 1)
+            for mode in (0, 1):
+                got = F.pack_weight(w3, mode, cop, cip)
+                assert got.shape == want[(i, mode)].shape
+                assert torch.equal(got, want[(i, mode)]), (i, mode)
