@@ -106,7 +106,9 @@ __device__ __forceinline__ void store_row_from_tmem(uint32_t taddr_row, int col,
 }
 
 // =================================================================================================== forward
-__global__ void __launch_bounds__(128)
+// 256 threads: two threads per query row split the columns of the softmax and of the output drain (see the
+// backward kernel); the row maximum and the row sum are combined through a small shared-memory exchange.
+__global__ void __launch_bounds__(256)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                 const __grid_constant__ AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -154,11 +156,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   mbar_wait(bar_mma, 0);
   tc_fence_after();
 
-  // ---- softmax, thread = query row ----
-  const uint32_t trow = tmem + (static_cast<uint32_t>(tid) << 16);  // lane = tid (warp w owns lanes 32w..32w+31)
-  const int t = t0 + tid;
+  // ---- softmax, two threads per query row (half = column range) ----
+  const int row = tid & 127, half = tid >> 7;
+  const uint32_t trow = tmem + (static_cast<uint32_t>(row) << 16);  // lane = row (warp w owns lanes 32(w%4)..)
+  float* xch = reinterpret_cast<float*>(smem + a.off_bar + 64);  // [max | sum][half][128 rows]
+  const int nch_s = a.Tp >> 5, nch_d = a.d >> 5;
+  const int cs0 = half ? (nch_s + 1) / 2 * 32 : 0, cs1 = half ? a.Tp : (nch_s + 1) / 2 * 32;
+  const int cd0 = half ? (nch_d + 1) / 2 * 32 : 0, cd1 = half ? a.d : (nch_d + 1) / 2 * 32;
+  const int t = t0 + row;
   float mx = -INFINITY;
-  for (int c = 0; c < a.Tp; c += 32) {
+  for (int c = cs0; c < cs1; c += 32) {
     uint32_t r[32];
     tmem_ld32(trow + c, r);
     tmem_ld_wait();
@@ -166,9 +173,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int j = 0; j < 32; ++j)
       if (c + j < a.T) mx = fmaxf(mx, __uint_as_float(r[j]));
   }
+  xch[half * 128 + row] = mx;
+  __syncthreads();
+  mx = fmaxf(xch[row], xch[128 + row]);
   float sum = 0.f;
   const float mxs = mx * a.scale_log2e;
-  for (int c = 0; c < a.Tp; c += 32) {
+  for (int c = cs0; c < cs1; c += 32) {
     uint32_t r[32];
     float p[32];
     tmem_ld32(trow + c, r);
@@ -178,12 +188,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       p[j] = (c + j < a.T) ? exp2f(__uint_as_float(r[j]) * a.scale_log2e - mxs) : 0.f;
       sum += p[j];
     }
-    store_p32(smem + a.off_p, tid, c, p);  // aliases Q|K, which the S MMA has finished reading
+    store_p32(smem + a.off_p, row, c, p);  // aliases Q|K, which the S MMA has finished reading
   }
+  xch[256 + half * 128 + row] = sum;
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  sum = xch[256 + row] + xch[384 + row];
   if (tid == 0) {
     const uint32_t idesc = make_idesc_bf16(128, a.d, 0, 1);
     for (int kk = 0; kk < a.Tp / 16; ++kk)
@@ -194,8 +206,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   const bool valid = t < a.T;
   bf16* dst = a.y + (static_cast<size_t>(b) * a.T + (valid ? t : 0)) * a.C + h * a.d;
-  store_row_from_tmem(trow, 0, a.d, 1.f / sum, dst, valid);
-  if (valid && a.lse) a.lse[(static_cast<size_t>(b) * a.heads + h) * a.T + t] = mx * a.scale + logf(sum);
+  if (cd0 < cd1) store_row_from_tmem(trow, cd0, cd1 - cd0, 1.f / sum, dst + cd0, valid);
+  if (valid && a.lse && half == 0) a.lse[(static_cast<size_t>(b) * a.heads + h) * a.T + t] = mx * a.scale + logf(sum);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -205,7 +217,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 // =================================================================================================== backward
-__global__ void __launch_bounds__(128)
+// 256 threads: two threads per query row (thread = row + 128*half) split the COLUMNS of every elementwise phase
+// (P = exp(S - lse), dS = P*(dP - D), the dQ/dK/dV drains); a warp may only touch the TMEM lanes of its quadrant
+// (warp % 4), which is exactly row / 32 for both halves.  With 128 threads these phases, not the five GEMMs, set the
+// kernel's time.
+__global__ void __launch_bounds__(256)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                 const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -215,6 +231,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* bar_mma = bar_kv + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_kv + 3);
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = tid & 127, half = tid >> 7;
   const int h = blockIdx.x % a.heads, b = blockIdx.x / a.heads;
   const int ns = (a.Tp + 127) / 128;  // key tiles of 128
   const int r0w = a.Tp > a.d ? a.Tp : a.d;
@@ -236,7 +253,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   pdl_wait();
   const uint32_t sQ = smem_u32(smem + a.off_q), sDO = smem_u32(smem + a.off_do), sK = smem_u32(smem + a.off_k),
                  sV = smem_u32(smem + a.off_v), sP = smem_u32(smem + a.off_p);
-  const uint32_t trow = tmem + (static_cast<uint32_t>(tid) << 16);
+  const uint32_t trow = tmem + (static_cast<uint32_t>(row) << 16);
+  // column ranges of this half: 32-column chunks of the [128 x Tp] score tile and of the d-wide accumulators
+  const int nch_s = a.Tp >> 5, nch_d = a.d >> 5;
+  const int cs0 = half ? (nch_s + 1) / 2 * 32 : 0, cs1 = half ? a.Tp : (nch_s + 1) / 2 * 32;
+  const int cd0 = half ? (nch_d + 1) / 2 * 32 : 0, cd1 = half ? a.d : (nch_d + 1) / 2 * 32;
   const int cq = h * 3 * a.d;
   uint32_t mma_phase = 0;
 
@@ -250,7 +271,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   for (int qt = 0; qt < a.nqt; ++qt) {
     const int t0 = qt * 128;
-    const int t = t0 + tid;
+    const int t = t0 + row;
     const bool valid = t < a.T;
     if (tid == 0) {
       mbar_expect_tx(bar_q, 2 * 128 * a.d * 2);
@@ -287,7 +308,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_after();
     // P = exp(S*scale - lse)
     const float lse2 = lse * 1.4426950408889634f;
-    for (int c = 0; c < a.Tp; c += 32) {
+    for (int c = cs0; c < cs1; c += 32) {
       uint32_t r[32];
       float p[32];
       tmem_ld32(trow + c, r);
@@ -295,7 +316,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         p[j] = (valid && c + j < a.T) ? exp2f(__uint_as_float(r[j]) * a.scale_log2e - lse2) : 0.f;
-      store_p32(smem + a.off_p, tid, c, p);
+      store_p32(smem + a.off_p, row, c, p);
     }
     fence_proxy_async();
     tc_fence_before();
@@ -316,15 +337,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mma_phase ^= 1;
     tc_fence_after();
     // dS = P * (dP - D) * scale, in place over P
-    for (int c = 0; c < a.Tp; c += 32) {
+    for (int c = cs0; c < cs1; c += 32) {
       uint32_t r[32];
       float p[32];
       tmem_ld32(trow + c, r);
       tmem_ld_wait();
-      load_p32(smem + a.off_p, tid, c, p);
+      load_p32(smem + a.off_p, row, c, p);
 #pragma unroll
       for (int j = 0; j < 32; ++j) p[j] = p[j] * (__uint_as_float(r[j]) - Dt) * a.scale;
-      store_p32(smem + a.off_p, tid, c, p);
+      store_p32(smem + a.off_p, row, c, p);
     }
     fence_proxy_async();
     tc_fence_before();
@@ -345,17 +366,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mma_phase ^= 1;
     tc_fence_after();
     bf16* dq = a.y + (static_cast<size_t>(b) * a.T + (valid ? t : 0)) * (3 * a.C) + cq;
-    if (do_v) store_row_from_tmem(trow, 0, a.d, 1.f, dq, valid);
+    if (do_v && cd0 < cd1) store_row_from_tmem(trow, cd0, cd1 - cd0, 1.f, dq + cd0, valid);
     tc_fence_before();
     __syncthreads();  // R0 and the Q/dO tiles are free for the next query tile
     tc_fence_after();
   }
   for (int j = 0; j < ns; ++j) {
-    const int s = j * 128 + tid;
+    const int s = j * 128 + row;
     const bool valid = s < a.T;
     bf16* base = a.y + (static_cast<size_t>(b) * a.T + (valid ? s : 0)) * (3 * a.C) + cq;
-    if (do_k) store_row_from_tmem(trow, col_dk + j * a.d, a.d, 1.f, base + a.d, valid);
-    if (do_v) store_row_from_tmem(trow, col_dv + j * a.d, a.d, 1.f, base + 2 * a.d, valid);
+    if (cd0 < cd1) {
+      if (do_k) store_row_from_tmem(trow, col_dk + j * a.d + cd0, cd1 - cd0, 1.f, base + a.d + cd0, valid);
+      if (do_v) store_row_from_tmem(trow, col_dv + j * a.d + cd0, cd1 - cd0, 1.f, base + 2 * a.d + cd0, valid);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -407,7 +430,7 @@ extern "C" int pddm_attn_fwd(const pddm_attn_fwd_params* p, pddm_stream_t s_) {
   const uint32_t region_a = (q_bytes + kv_bytes) > p_bytes ? (q_bytes + kv_bytes) : p_bytes;
   a.off_q = 0; a.off_k = q_bytes; a.off_p = 0; a.off_v = (region_a + 1023) / 1024 * 1024;
   a.off_bar = a.off_v + (kv_bytes + 1023) / 1024 * 1024;
-  const size_t smem = a.off_bar + 64 + 1024;
+  const size_t smem = a.off_bar + 64 + 2048 + 1024;  // barriers, softmax exchange, alignment slack
   uint32_t cols = 32;
   const uint32_t need = a.Tp > a.d ? a.Tp : a.d;
   while (cols < need) cols <<= 1;
@@ -419,7 +442,7 @@ extern "C" int pddm_attn_fwd(const pddm_attn_fwd_params* p, pddm_stream_t s_) {
   if (cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            device_info().max_smem_optin) != cudaSuccess)
     return PDDM_ERR_CUDA;
-  PdlLaunch(a.B * a.heads * a.nqt, 128, smem, s)(attn_fwd_kernel, tmQ, tmKV, a);
+  PdlLaunch(a.B * a.heads * a.nqt, 256, smem, s)(attn_fwd_kernel, tmQ, tmKV, a);
   return launch_status();
 }
 
@@ -465,13 +488,13 @@ extern "C" int pddm_attn_bwd(const pddm_attn_bwd_params* p, pddm_stream_t s_) {
     return PDDM_ERR_CUDA;
   if (!two_pass) {
     a.pass = 0;
-    PdlLaunch(a.B * a.heads, 128, smem, s)(attn_bwd_kernel, tmQ, tmKV, tmDO, a);
+    PdlLaunch(a.B * a.heads, 256, smem, s)(attn_bwd_kernel, tmQ, tmKV, tmDO, a);
   } else {
     a.pass = 1;
-    PdlLaunch(a.B * a.heads, 128, smem, s)(attn_bwd_kernel, tmQ, tmKV, tmDO, a);
+    PdlLaunch(a.B * a.heads, 256, smem, s)(attn_bwd_kernel, tmQ, tmKV, tmDO, a);
     if (cudaPeekAtLastError() != cudaSuccess) return PDDM_ERR_CUDA;
     a.pass = 2;
-    PdlLaunch(a.B * a.heads, 128, smem, s)(attn_bwd_kernel, tmQ, tmKV, tmDO, a);
+    PdlLaunch(a.B * a.heads, 256, smem, s)(attn_bwd_kernel, tmQ, tmKV, tmDO, a);
   }
   return launch_status();
 }

@@ -10,6 +10,7 @@ each step; ~0.1 ms per step for 49 M parameters).  Inside ``frozen_weights()`` (
 are cached per parameter version.
 """
 import contextlib
+import weakref
 from typing import Optional, Tuple
 
 import torch
@@ -45,8 +46,14 @@ def _packed(w, mode):
     key = (w.data_ptr(), mode)
     ent = _PACK_CACHE.get(key)
     stamp = (w._version, _EPOCH[0], tuple(w.shape))
-    if ent is None or ent[0] != stamp:
-        ent = (stamp, F.pack_weight(w, mode))
+    # the weak reference ties the entry to this very tensor object: a freed parameter's address can be handed to a
+    # new parameter of the same shape and version (another model built later in the process)
+    owner = w._base if w._base is not None else w  # views (linear weights seen as [N, K, 1]) belong to their base
+    if ent is None or ent[0] != stamp or ent[2]() is not owner:
+        if len(_PACK_CACHE) > 4096:  # entries of dead tensors
+            for k in [k for k, e in _PACK_CACHE.items() if e[2]() is None]:
+                del _PACK_CACHE[k]
+        ent = (stamp, F.pack_weight(w, mode), weakref.ref(owner))
         _PACK_CACHE[key] = ent
     return ent[1]
 

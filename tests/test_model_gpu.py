@@ -127,3 +127,18 @@ def test_unet_celeba64_config_trains():
     errs = {n: rel(got[n].grad, Pr[n].grad) for n in Pr if float(Pr[n].grad.norm()) > 1e-3}
     bad = {n: round(v, 3) for n, v in errs.items() if v > 0.1}
     assert not bad, bad
+
+
+def test_frozen_weight_cache_is_tied_to_the_tensor_object():
+    """A cached pack must not survive its parameter: the allocator hands a freed parameter's address to the next
+    tensor of the same shape (a second model built later in the process), with the same version counter."""
+    from probabilisticdeepdiffusionmodels_b200 import ops
+    x = torch.randn(2, 8, 8, 64, device="cuda").bfloat16()
+    outs = []
+    for seed in (1, 2):
+        w = torch.empty(64, 64, 3, 3, device="cuda")  # same size -> same block of the caching allocator
+        w.copy_(torch.randn(64, 64, 3, 3, generator=torch.Generator().manual_seed(seed)) * 0.05)
+        with torch.no_grad(), ops.frozen_weights():
+            outs.append((torch.ops.pddm.conv2d(x, w, None, None, None, 1, False)[0].float().clone(), w.data_ptr()))
+        del w
+    assert not torch.equal(outs[0][0], outs[1][0])
