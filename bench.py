@@ -198,6 +198,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--bucketed-allreduce", action="store_true",
+                    help="N>1: all-reduce bucket by bucket from inside backward on a communication stream")
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (weak scaling)")
     ap.add_argument("--sample-steps", type=int, default=1000, help="length of the timed reverse chain")
     ap.add_argument("--no-sampling", action="store_true")
@@ -249,7 +251,13 @@ def main():
     g = torch.Generator().manual_seed(1234 + rank)
     host_x = (torch.rand((B, 3, RES, RES), generator=g) * 2 - 1).pin_memory()
     x_dev = host_x.to(dev)
-    hook = parallel.FlatGradAllReduce() if world > 1 else None
+    # gradient averaging: one flat all-reduce between backward and Adam.  --bucketed-allreduce issues it bucket by
+    # bucket from inside backward on a communication stream; measured equal at 2 GPUs (the persistent GEMM kernels
+    # leave NCCL no SM to overlap on), so the simpler form is the default.
+    hook = None
+    if world > 1:
+        hook = parallel.BucketedGradAllReduce(eng.model.parameters()) if args.bucketed_allreduce else \
+            parallel.FlatGradAllReduce()
 
     step = eng.capture_train_step((B, 3, RES, RES), grad_hook=hook, overlap_wgrad=not args.no_overlap)
     kernels_per_step = step.state["kernels_per_step"]  # this library's kernels inside one captured step
@@ -314,14 +322,28 @@ def main():
                     "finite": bool(torch.isfinite(out).all())}
 
     def finish():
-        # Multi-rank teardown: leave without running the NCCL communicator destructors.  Both
-        # dist.destroy_process_group() and a plain interpreter exit were observed to hang here once the captured
-        # step (NCCL all-reduce node + side-stream weight-gradient branch) had been replayed; every collective of
-        # the run has completed by now (max-over-ranks reductions above), so nothing is lost.
+        # Multi-rank teardown.  dist.destroy_process_group() and a plain interpreter exit were both observed to hang
+        # here once the captured step (NCCL all-reduce node + side-stream weight-gradient branch) had been replayed,
+        # so every rank leaves through os._exit.  The other ranks first wait (on the rendezvous store, not on NCCL)
+        # until rank 0 has printed its line: a rank that disappears while rank 0 is still timing the roofline census
+        # can get rank 0 torn down by the NCCL watchdog.
         if world > 1:
             torch.cuda.synchronize(dev)
+            try:
+                store = dist.distributed_c10d._get_default_store()
+                if rank == 0:
+                    store.set("pddm_bench_done", "1")
+                    time.sleep(0.5)  # let the waiters read the key before the store's server (this process) exits
+                else:
+                    store.wait(["pddm_bench_done"], __import__("datetime").timedelta(seconds=600))
+            except Exception:
+                pass
             sys.stdout.flush()
             sys.stderr.flush()
+            try:
+                __import__("ctypes").CDLL(None).fflush(None)  # C stdio buffers (NCCL's banner) are not flushed by _exit
+            except Exception:
+                pass
             os._exit(0)
 
     if rank != 0:

@@ -66,6 +66,117 @@ class FlatGradAllReduce:
         torch._foreach_copy_(grads, views)
 
 
+class BucketedGradAllReduce:
+    """Gradient averaging that overlaps the backward pass: ``hook = BucketedGradAllReduce(params)`` registers a
+    post-accumulate-grad hook on every parameter; as soon as the gradients of one bucket (parameters in the order
+    their gradients become ready, ~32 MB of fp32 each) are complete, the bucket is copied into its slice of ONE flat
+    buffer and all-reduced on a communication stream while autograd keeps producing the next bucket.  Calling
+    ``hook(params)`` after ``backward()`` joins the communication stream and points every ``p.grad`` at its
+    (averaged) slice of the flat buffer -- no copy back.  The first backward only learns the ready order and
+    reduces everything at the end.  Works eagerly, under CUDA-graph capture (fork / join become graph edges) and on
+    CPU tensors with gloo (no streams).  With the weight-gradient GEMMs on a side stream (``ops.overlap_wgrad``) the
+    communication stream also waits for that stream."""
+
+    def __init__(self, params, bucket_bytes=32 << 20, group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        self.bucket_bytes = bucket_bytes
+        self._fired = []
+        self.buckets = None  # list of lists of param indices
+        self.handles = [p.register_post_accumulate_grad_hook(self._make_hook(i)) for i, p in enumerate(self.params)]
+        self.comm = None
+
+    def _active(self):
+        return dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _make_hook(self, i):
+        def hook(_p):
+            if not self._active():
+                return
+            if self.buckets is None:
+                self._fired.append(i)
+                return
+            b = self.bucket_of[i]
+            self.pending[b] -= 1
+            if self.pending[b] == 0:
+                self._launch(b)
+        return hook
+
+    def _build(self):
+        order = list(dict.fromkeys(self._fired))
+        order += [i for i in range(len(self.params)) if i not in set(order) and self.params[i].grad is not None]
+        self.buckets, cur, size = [], [], 0
+        for i in order:
+            cur.append(i)
+            size += self.params[i].numel() * 4
+            if size >= self.bucket_bytes:
+                self.buckets.append(cur)
+                cur, size = [], 0
+        if cur:
+            self.buckets.append(cur)
+        self.bucket_of = {i: b for b, idx in enumerate(self.buckets) for i in idx}
+        dev = self.params[order[0]].device
+        n = sum(self.params[i].numel() for i in order)
+        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        self.views, self.slices, off = [], [], 0
+        for idx in self.buckets:
+            o0, vs = off, []
+            for i in idx:
+                p = self.params[i]
+                vs.append(self.flat[off: off + p.numel()].view_as(p))
+                off += p.numel()
+            self.views.append(vs)
+            self.slices.append(self.flat[o0: off])
+        if dev.type == "cuda":
+            self.comm = torch.cuda.Stream(device=dev)
+        self._reset()
+
+    def _reset(self):
+        self.pending = [len(idx) for idx in self.buckets]
+        self.launched = [False] * len(self.buckets)
+
+    def _launch(self, b):
+        grads = [self.params[i].grad for i in self.buckets[b]]
+        inv = 1.0 / dist.get_world_size(self.group)
+        if self.comm is not None:
+            from . import ops
+            cur = torch.cuda.current_stream(self.flat.device)
+            self.comm.wait_stream(cur)
+            side = ops._OVERLAP["side"]
+            if ops._OVERLAP["on"] and side is not None:
+                self.comm.wait_stream(side)  # weight gradients are written by GEMMs on the side stream
+            with torch.cuda.stream(self.comm):
+                torch._foreach_copy_(self.views[b], grads)
+                dist.all_reduce(self.slices[b], op=dist.ReduceOp.SUM, group=self.group)
+                self.slices[b].mul_(inv)
+        else:
+            torch._foreach_copy_(self.views[b], grads)
+            dist.all_reduce(self.slices[b], op=dist.ReduceOp.SUM, group=self.group)
+            self.slices[b].mul_(inv)
+        self.launched[b] = True
+
+    def __call__(self, params=None):
+        if not self._active():
+            return
+        if self.buckets is None:
+            self._build()
+        for b in range(len(self.buckets)):  # learning pass, or parameters whose gradient never arrived
+            if not self.launched[b]:
+                if any(self.params[i].grad is None for i in self.buckets[b]):
+                    raise RuntimeError("BucketedGradAllReduce: a parameter of the recorded set received no gradient")
+                self._launch(b)
+        if self.comm is not None:
+            torch.cuda.current_stream(self.flat.device).wait_stream(self.comm)
+        for b, idx in enumerate(self.buckets):
+            for i, v in zip(idx, self.views[b]):
+                self.params[i].grad = v
+        self._reset()
+
+    def remove(self):
+        for h in self.handles:
+            h.remove()
+
+
 def broadcast_parameters(module, src=0, group=None):
     """Make every rank start from rank ``src``'s parameters and buffers."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:

@@ -55,6 +55,48 @@ def test_flat_grad_allreduce_equals_single_process_gradient(tmp_path):
     assert max(errs) < 1e-5, errs
 
 
+def _worker_bucketed(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from probabilisticdeepdiffusionmodels_b200 import parallel
+    parallel.init_from_env("gloo")
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 50), torch.nn.Tanh(), torch.nn.Linear(50, 40), torch.nn.Tanh(),
+                              torch.nn.Linear(40, 3))
+    params = list(net.parameters())
+    hook = parallel.BucketedGradAllReduce(params, bucket_bytes=4000)  # several buckets for this tiny net
+    x = torch.arange(8 * 6, dtype=torch.float32).reshape(8, 6) / 10.0
+    y = torch.arange(8 * 3, dtype=torch.float32).reshape(8, 3) / 5.0
+    xs, ys = parallel.shard_batch(x, rank, world), parallel.shard_batch(y, rank, world)
+    errs, nb = [], 0
+    for it in range(3):  # pass 0 learns the order, passes 1-2 reduce bucket by bucket from inside backward
+        for p in params:
+            p.grad = None
+        (((net(xs) - ys) ** 2).sum() / x.shape[0] * world).backward()
+        hook(params)
+        nb = len(hook.buckets)
+        ref = torch.nn.Sequential(torch.nn.Linear(6, 50), torch.nn.Tanh(), torch.nn.Linear(50, 40), torch.nn.Tanh(),
+                                  torch.nn.Linear(40, 3))
+        ref.load_state_dict(net.state_dict())
+        (((ref(x) - y) ** 2).sum() / x.shape[0]).backward()
+        errs.append(max(float((a.grad - b.grad).abs().max()) for a, b in zip(params, ref.parameters())))
+        with torch.no_grad():
+            for p in params:
+                p.add_(p.grad, alpha=-0.05)  # move, so that every pass has different gradients
+    if rank == 0:
+        torch.save({"errs": errs, "nb": nb}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bucketed_overlapped_allreduce_equals_single_process_gradient(tmp_path):
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_worker_bucketed, args=(2, _free_port(), out), nprocs=2, join=True)
+    res = torch.load(out)
+    assert res["nb"] >= 2
+    assert max(res["errs"]) < 1e-5, res
+
+
 def test_shard_batch_covers_everything():
     from probabilisticdeepdiffusionmodels_b200.parallel import shard_batch
     x = torch.arange(10)
