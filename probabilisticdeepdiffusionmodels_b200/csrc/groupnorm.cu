@@ -680,26 +680,43 @@ static bool make_slab_geom(int B, int HW, int C, int G, int nslabs, int nscratch
   *threads = g->CV * g->nlanes;
   const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
   const size_t budget = static_cast<size_t>(device_info().max_smem_optin) - 1024;
+  // Cluster size: measured over the model's shapes (profiles/r1_bench_gn_*.log, PDDM_GN_S sweeps), the kernel is
+  // fastest when a CTA holds about 64 KB of slabs (all of its slabs together): smaller CTAs pay their fixed cost
+  // (barriers, folds, cluster exchange) too often, larger ones leave one CTA per SM.  Among the feasible sizes pick
+  // the one closest to that; PDDM_GN_S forces an upper bound for experiments.
   const int smax = getenv("PDDM_GN_S") ? atoi(getenv("PDDM_GN_S")) : 8;
+  int best_S = 0;
+  long long best_dist = 0;
   for (int S = 8; S >= 1; S /= 2) {
     const int rows = (HW + S - 1) / S;
-    // a CTA wants >= 4 rows per lane to amortise its fixed cost (barriers, folds, cluster exchange)
+    // a CTA wants >= 4 rows per lane to amortise its fixed cost
     if (S > 1 && (S > smax || rows < 4 * g->nlanes || (S - 1) * rows >= HW || B * (S / 2) >= 8 * sms)) continue;
     const int slab = (rows * C * 2 + 127) / 128 * 128;
     const size_t need = static_cast<size_t>(nslabs) * slab +
                         (static_cast<size_t>(nscratch) * g->nlanes * C + 9 * C + 4 * G) * sizeof(float) +
                         kSlabChunks * sizeof(uint64_t);
-    if (need > budget) {
-      if (S == 8) return false;  // even the widest cluster does not fit
-      continue;
+    if (need > budget) continue;
+    long long dist = static_cast<long long>(nslabs) * slab - 64 * 1024;
+    if (dist < 0) dist = -dist;
+    if (best_S == 0 || dist < best_dist) {
+      best_S = S;
+      best_dist = dist;
     }
+  }
+  if (best_S == 0) return false;
+  {
+    const int S = best_S;
+    const int rows = (HW + S - 1) / S;
+    const int slab = (rows * C * 2 + 127) / 128 * 128;
     g->S = S;
     g->rows_per_cta = rows;
     g->slab_bytes = slab;
     int cr = (rows + kSlabChunks - 1) / kSlabChunks;
     cr = (cr + g->nlanes - 1) / g->nlanes * g->nlanes;
     g->chunk_rows = cr;
-    *smem = need;
+    *smem = static_cast<size_t>(nslabs) * slab +
+            (static_cast<size_t>(nscratch) * g->nlanes * C + 9 * C + 4 * G) * sizeof(float) +
+            kSlabChunks * sizeof(uint64_t);
     return true;
   }
   return false;
