@@ -5,9 +5,10 @@ under ``loss.backward()``, ``torch.no_grad()`` and CUDA-graph capture.  Tensors 
 contiguous NHWC bf16; the ops never fall back to eager torch math -- on a non-sm_100 device they raise.
 
 Weight operands: parameters stay fp32 ``nn.Parameter``s with the reference's names/shapes; the bf16 GEMM packs
-are produced by ``pddm_pack_conv_weight``.  While training they are re-packed on every call (weights change
-each step; ~0.1 ms per step for 49 M parameters).  Inside ``frozen_weights()`` (sampling / evaluation) packs
-are cached per parameter version.
+are produced by ``pddm_pack_conv_weight`` (eager training: re-packed on every call, the weights change each step),
+by ONE ``pddm_pack_weights_multi`` launch per step over a flat arena (``WeightArena``, the captured training step:
+0.28 ms for 49 M parameters), or cached per parameter object and version inside ``frozen_weights()`` (sampling /
+evaluation).
 """
 import contextlib
 import weakref
