@@ -140,7 +140,8 @@ def tap_wgrad(x, dy, taps, B, H, W, cin, cout, w_shape, accumulate_into=None, la
     st = L.stream() if launch_stream is None else C.c_void_p(launch_stream.cuda_stream)
     L.call("pddm_conv2d_wgrad", C.byref(p), L.ptr(ws), C.c_size_t(ws.numel()), st)
     if keep is not None:
-        keep.extend((ws, dw, x, dy))
+        keep.extend((ws, x, dy))  # NOT dw: an extra reference would make autograd's AccumulateGrad clone it (on the
+        # main stream, before the side-stream GEMM has written it) instead of adopting it as .grad
     return dw
 
 

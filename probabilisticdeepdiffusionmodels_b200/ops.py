@@ -69,7 +69,11 @@ def overlap_wgrad():
     A weight gradient is a leaf of the backward graph (only the optimiser consumes it), while the data gradient
     feeds the next GroupNorm backward; the wgrad kernel is TMA/tensor bound and light on registers, the GroupNorm /
     reduction kernels are LSU/L2 bound, so they co-reside on the SMs.  The streams are joined on exit (also valid
-    inside CUDA-graph capture: fork and join become graph edges).  Requires ``.grad is None`` on entry."""
+    inside CUDA-graph capture: fork and join become graph edges).  The gradient tensor must reach ``weight.grad`` without
+    any main-stream kernel touching it before the join: autograd's AccumulateGrad adopts it as is when ``.grad is None``
+    and nobody else holds a reference (which is why the keep-alive list below excludes it -- an extra reference made
+    AccumulateGrad clone the still unwritten buffer: found by tests/test_fullsize_gpu.py); parameters that already
+    carry a gradient fall back to the main stream."""
     cur = torch.cuda.current_stream()
     if _OVERLAP["side"] is None or _OVERLAP["side"].device != cur.device:
         _OVERLAP["side"] = torch.cuda.Stream(device=cur.device)
@@ -82,8 +86,10 @@ def overlap_wgrad():
         _OVERLAP["keep"].clear()
 
 
-def _wgrad(xin, dy, taps, B, H, W, Cin, Cout, shape):
-    if not _OVERLAP["on"]:
+def _wgrad(xin, dy, taps, B, H, W, Cin, Cout, shape, weight=None):
+    # The side-stream result is only safe if autograd ADOPTS it as ``weight.grad`` (no kernel).  If a gradient is
+    # already there autograd would accumulate into it on the main stream, racing with the GEMM: stay on the main stream.
+    if not _OVERLAP["on"] or (weight is not None and getattr(weight, "grad", None) is not None):
         return F.tap_wgrad(xin, dy, taps, B, H, W, Cin, Cout, shape)
     side = _OVERLAP["side"]
     side.wait_stream(torch.cuda.current_stream())  # dy / xin are ready
@@ -225,7 +231,7 @@ def conv2d_bwd(dy: Tensor, xin: Tensor, weight: Tensor, stride: int, upsample: b
         taps = F.taps_stride2(B)
     else:
         taps = F.taps_3x3() if k == 3 else F.taps_1x1()
-    dw = _wgrad(xin, dy, taps, B, H, W, Cin, Cout, tuple(weight.shape))
+    dw = _wgrad(xin, dy, taps, B, H, W, Cin, Cout, tuple(weight.shape), weight)
     dbias = F.colsum(dy, Cout) if need_dbias else _empty(dy)
     dbcast = F.colsum_per_sample(dy) if need_dbcast else _empty(dy)
     dx = _empty(dy)
