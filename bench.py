@@ -234,17 +234,20 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from oracle.unet_ref import MODEL_CONFIGS, arch_from_config, fwd_flops_per_image, make_params
+    # (nothing on this arm imports oracle/: configurations, the synthetic initialisation and the FLOP counter
+    #  live in the package; the oracle is only executed by the cpu_baseline / --impl reference leg above)
     from probabilisticdeepdiffusionmodels_b200 import Engine, _lib, parallel
+    from probabilisticdeepdiffusionmodels_b200.configs import MODEL_CONFIGS, synthetic_init_, unet_fwd_flops_per_image
 
     rank, world, local_rank = parallel.init_from_env("nccl")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     cfg = MODEL_CONFIGS[MODEL]
-    arch = arch_from_config(RES, **{k: v for k, v in cfg.items() if k != "name"}, learn_sigma=True)
+    torch.manual_seed(1)
     eng = Engine(dict(cfg), {"lr": 1e-4}, diffusion_steps=1000, mode="cosine", resolution=RES,
                  clip_while_generating=True, learn_sigma=True, log_loss_per_t=False)
-    eng.model.load_state_dict(make_params(arch, seed=1))  # random init incl. the reference's zero-init convs
+    synthetic_init_(eng.model, seed=1)  # random init incl. the reference's zero-init convs
+    fwd_flops = unet_fwd_flops_per_image(eng.model, RES)
     eng = eng.to(dev)
     parallel.broadcast_parameters(eng.model)
     B = args.batch
@@ -350,7 +353,7 @@ def main():
         finish()
         return
     burst, sustained, hbm, src = peaks()
-    fwd = fwd_flops_per_image(arch, RES)
+    fwd = fwd_flops
     train_flops = 3 * fwd
     achieved = img_s / world * train_flops / 1e12  # per GPU
     roof_step = {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",

@@ -198,3 +198,20 @@ def test_nn_factories_keep_reference_contract():
     y = N.checkpoint(lambda a: a * 3, (x,), (), True)
     y.sum().backward()
     assert x.grad.tolist() == [3.0, 3.0]
+
+
+def test_package_configs_and_flop_counter_agree_with_the_oracle():
+    """configs.MODEL_CONFIGS mirrors the oracle's copy of config/model/*.yaml, and the module-walking FLOP counter
+    bench.py uses (nothing on the measured path imports oracle/) equals the oracle's block-plan formula."""
+    from oracle.unet_ref import MODEL_CONFIGS as REF, arch_from_config, fwd_flops_per_image
+    from probabilisticdeepdiffusionmodels_b200.configs import MODEL_CONFIGS, synthetic_init_, unet_fwd_flops_per_image
+    from probabilisticdeepdiffusionmodels_b200.modules import get_unet
+    assert MODEL_CONFIGS == REF
+    for name, res, ls in [("unet", 32, True), ("unet", 32, False), ("unet_small_grey", 28, False),
+                          ("unet_celeba", 64, False), ("unet_grey", 32, False)]:
+        kw = {k: v for k, v in MODEL_CONFIGS[name].items() if k != "name"}
+        m = get_unet(res, **kw, learn_sigma=ls)
+        arch = arch_from_config(res, **kw, learn_sigma=ls)
+        assert unet_fwd_flops_per_image(m, res) == fwd_flops_per_image(arch, res), name
+    m = synthetic_init_(get_unet(28, **{k: v for k, v in MODEL_CONFIGS["unet_small_grey"].items() if k != "name"}), 3)
+    assert all(float(p.abs().sum()) > 0 for p in m.parameters() if p.dim() > 1)

@@ -7,15 +7,14 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle.unet_ref import MODEL_CONFIGS, arch_from_config, make_params  # noqa: E402
 from probabilisticdeepdiffusionmodels_b200 import Engine  # noqa: E402
+from probabilisticdeepdiffusionmodels_b200.configs import MODEL_CONFIGS, synthetic_init_  # noqa: E402
 
 B = int(os.environ.get("PDDM_B", "128"))
 cfg = MODEL_CONFIGS["unet"]
-arch = arch_from_config(32, **{k: v for k, v in cfg.items() if k != "name"}, learn_sigma=True)
 eng = Engine(dict(cfg), {"lr": 1e-4}, mode="cosine", resolution=32, clip_while_generating=True, learn_sigma=True,
              log_loss_per_t=False)
-eng.model.load_state_dict(make_params(arch, seed=1))
+synthetic_init_(eng.model, seed=1)
 eng = eng.cuda()
 x = torch.rand(B, 3, 32, 32, device="cuda") * 2 - 1
 step = eng.capture_train_step((B, 3, 32, 32))
