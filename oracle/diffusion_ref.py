@@ -99,7 +99,7 @@ def timestep_embedding(timesteps, dim, max_period=10000):
     """src/modules/nn.py:104-122 -- [cos | sin], zero pad if dim is odd."""
     half = dim // 2
     freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
-    args = timesteps[:, None].float() * freqs[None]
+    args = timesteps[:, None].float() * freqs[None].to(timesteps.device)  # (.to(device): src/modules/nn.py:116)
     emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
     if dim % 2:
         emb = torch.cat([emb, torch.zeros_like(emb[:, :1])], dim=-1)
