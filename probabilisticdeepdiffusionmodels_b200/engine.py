@@ -28,7 +28,8 @@ from . import ops
 from .mathutils import get_generator_if_specified, mean_flat
 from .modules import get_model
 from .schedules import TABLE_NAMES, get_betas, make_tables
-from .timesteps import ImportanceSampler, StepwiseLog, UniformSampler
+from .timesteps import (DeviceImportanceSampler, DeviceStepwiseLog, ImportanceSampler, StepwiseLog,
+                        UniformSampler)
 from .weight_average import Ema
 
 try:  # the reference subclasses pl.LightningModule; fall back to a minimal stand-in when Lightning is absent
@@ -94,10 +95,16 @@ class Engine(_Base):
             setattr(self, name, self._tables[name])
         self._dev_tables = {}
 
-        self.loss_per_t = StepwiseLog(diffusion_steps, 10)
-        self.loss_per_t_epoch = StepwiseLog(diffusion_steps)
+        if log_loss_per_t == "device":  # extension: statistics live on the device, no per-step host sync
+            self.loss_per_t = DeviceStepwiseLog(diffusion_steps, 10)
+            self.loss_per_t_epoch = DeviceStepwiseLog(diffusion_steps)
+        else:
+            self.loss_per_t = StepwiseLog(diffusion_steps, 10)
+            self.loss_per_t_epoch = StepwiseLog(diffusion_steps)
         if sampling == "uniform":
             self.sampler = UniformSampler(diffusion_steps=diffusion_steps)
+        elif sampling == "importance" and log_loss_per_t == "device":
+            self.sampler = DeviceImportanceSampler(diffusion_steps, self.loss_per_t, min_counts=10)
         elif sampling == "importance":
             self.sampler = ImportanceSampler(diffusion_steps=diffusion_steps, loss_per_t=self.loss_per_t, min_counts=10)
         else:
@@ -183,26 +190,43 @@ class Engine(_Base):
             return per
         return torch.ops.pddm.simple_loss(model_out, target_noise)
 
-    def get_loss(self, predicted_noise, target_noise, x, x_t, t, weights=None, update_loss_log=True):
-        """src/engine.py:263-277"""
+    def get_loss(self, predicted_noise, target_noise, x, x_t, t, weights=None, update_loss_log=True, ready=None):
+        """src/engine.py:263-277.  ``ready`` (0-dim bool tensor, device importance sampler): weight the batch only once
+        the sampler is warmed up, average before -- decided on the device."""
         loss = self.per_sample_loss(predicted_noise, target_noise, x, x_t, t)
-        if update_loss_log and self.log_loss_per_t:
+        if update_loss_log and self.log_loss_per_t == "device":
+            for log in (self.loss_per_t, self.loss_per_t_epoch):
+                if log.device != loss.device:
+                    log.to(loss.device)
+                log.update_multiple(t, loss.detach())
+        elif update_loss_log and self.log_loss_per_t:
             losses = loss.detach().cpu().numpy().tolist()  # the reference's per-step host sync
             ts = t.detach().cpu().numpy().tolist()
             self.loss_per_t.update_multiple(ts, losses)
             self.loss_per_t_epoch.update_multiple(ts, losses)
+        if ready is not None:
+            return torch.where(ready, torch.sum(weights * loss), torch.mean(loss).to(weights.dtype))
         if weights is not None:
             return torch.sum(weights * loss)
         return torch.mean(loss)
 
+    def _draw_timesteps(self, batch_size):
+        """-> (t, weights | None, ready | None) from either kind of sampler"""
+        if isinstance(self.sampler, DeviceImportanceSampler):
+            if self.loss_per_t.device != self.device:
+                self.loss_per_t.to(self.device)
+            return self.sampler(batch_size)
+        t, weights = self.sampler(batch_size, self.device)
+        return t, weights, None
+
     def training_step(self, batch, batch_idx):  # pylint: disable=unused-argument
         """src/engine.py:279-307"""
         x, y = batch
-        t, weights = self.sampler(x.shape[0], self.device)
+        t, weights, ready = self._draw_timesteps(x.shape[0])
         noise = torch.randn_like(x)
         x_t = self.get_q_t(x, noise, t)
         predicted_noise = self.model(x_t, t)
-        loss = self.get_loss(predicted_noise, noise, x, x_t, weights=weights, t=t, update_loss_log=True)
+        loss = self.get_loss(predicted_noise, noise, x, x_t, weights=weights, t=t, update_loss_log=True, ready=ready)
         total_norm = self.compute_grad_norm(self.model.parameters())
         self.log("loss", loss, on_step=False, on_epoch=True, prog_bar=True)
         self.log("total_grad_norm_L2", total_norm, on_step=True, on_epoch=False, prog_bar=False)
@@ -532,10 +556,23 @@ class Engine(_Base):
 
         arena = ops.WeightArena()
 
+        device_log = self.log_loss_per_t == "device"
+
         def fwd_bwd():
-            t = torch.randint(1, self.diffusion_steps + 1, (batch_shape[0],), device=dev)
             noise = torch.randn_like(st["x"])
-            loss, per = self.loss_on(st["x"], t, noise)
+            if device_log:  # timestep draw (uniform or importance), loss weighting and loss log all inside the graph
+                t, weights, ready = self._draw_timesteps(batch_shape[0])
+                x_t = self.get_q_t(st["x"], noise, t)
+                per = self.per_sample_loss(self.model(x_t, t), noise, st["x"], x_t, t)
+                for log in (self.loss_per_t, self.loss_per_t_epoch):
+                    if log.device != per.device:
+                        log.to(per.device)
+                    log.update_multiple(t, per.detach())
+                loss = torch.mean(per) if ready is None else \
+                    torch.where(ready, torch.sum(weights * per), torch.mean(per).to(weights.dtype))
+            else:
+                t = torch.randint(1, self.diffusion_steps + 1, (batch_shape[0],), device=dev)
+                loss, per = self.loss_on(st["x"], t, noise)
             if overlap_wgrad:
                 with ops.overlap_wgrad():  # weight-gradient GEMMs on a side stream, joined before the optimiser
                     loss.backward()

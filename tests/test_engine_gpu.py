@@ -183,3 +183,22 @@ def test_captured_train_step_is_bitwise_reproducible():
     lb, pb = run()
     assert la == lb
     assert all(torch.equal(a, b) for a, b in zip(pa, pb))
+
+
+def test_captured_step_with_device_side_loss_log_and_importance_sampler():
+    """the per-timestep loss history and the loss-aware timestep sampler live on the device, so the
+    whole step -- draw t, weight the loss, update the history -- replays as one CUDA graph with no host sync."""
+    eng = make_engine("cosine", steps=20, log_loss_per_t="device", sampling="importance")
+    B = 16
+    x = torch.rand(B, 1, 28, 28, device="cuda") * 2 - 1
+    step = eng.capture_train_step(tuple(x.shape))
+    n0 = float(eng.loss_per_t.n_per_step.sum())  # warm-up iterations of the capture already logged
+    assert not bool(eng.sampler._ready) or n0 > 0
+    losses = [float(step(x)) for _ in range(40)]
+    assert np.isfinite(losses).all()
+    n1 = float(eng.loss_per_t.n_per_step.sum())
+    assert n1 - n0 == 40 * B  # state advances across replays (in-place updates of persistent tensors)
+    assert bool(eng.sampler._ready)  # every timestep has >= 10 samples by now: importance sampling switched on
+    assert float(eng.loss_per_t.avg_sq_per_step.min()) > 0
+    # after the switch the loss is the reference's weighted SUM (weights 1/(p_t B)), i.e. of order the mean again
+    assert 0 < np.mean(losses[-5:]) < 10 * max(np.mean(losses[:5]), 1e-3) + 10

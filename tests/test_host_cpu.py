@@ -215,3 +215,53 @@ def test_package_configs_and_flop_counter_agree_with_the_oracle():
         assert unet_fwd_flops_per_image(m, res) == fwd_flops_per_image(arch, res), name
     m = synthetic_init_(get_unet(28, **{k: v for k, v in MODEL_CONFIGS["unet_small_grey"].items() if k != "name"}), 3)
     assert all(float(p.abs().sum()) > 0 for p in m.parameters() if p.dim() > 1)
+
+
+@pytest.mark.parametrize("max_keep", [None, 3, 50])
+def test_device_stepwise_log_matches_host_log(max_keep):
+    """DeviceStepwiseLog (batched tensor updates, no host loop) reproduces StepwiseLog's running mean / RMS / count,
+    including duplicates of a timestep inside one batch, the max_keep truncation rule and skipped non-finite values."""
+    import numpy as np
+    from probabilisticdeepdiffusionmodels_b200.timesteps import DeviceStepwiseLog, StepwiseLog
+    T = 12
+    host, dev = StepwiseLog(T, max_keep), DeviceStepwiseLog(T, max_keep)
+    rs = np.random.RandomState(3)
+    for it in range(25):
+        B = int(rs.randint(1, 20))
+        ts = rs.randint(1, T + 1, size=B)
+        if it % 5 == 0:
+            ts[:] = ts[0]  # many duplicates of one timestep (more than max_keep=3)
+        ms = rs.rand(B) * 3
+        if it % 7 == 0:
+            ms[0] = np.inf
+        host.update_multiple(ts.tolist(), ms.tolist())
+        dev.update_multiple(torch.from_numpy(ts), torch.from_numpy(ms))
+        np.testing.assert_allclose(dev.n_per_step.numpy(), host.n_per_step)
+        np.testing.assert_allclose(dev.avg_per_step.numpy(), host.avg_per_step, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(dev.avg_sq_per_step.numpy(), host.avg_sq_per_step, rtol=1e-12, atol=1e-12)
+
+
+def test_device_importance_sampler_warmup_and_weights():
+    import numpy as np
+    from probabilisticdeepdiffusionmodels_b200.timesteps import (DeviceImportanceSampler, DeviceStepwiseLog,
+                                                                 ImportanceSampler, StepwiseLog)
+    T = 6
+    hlog, dlog = StepwiseLog(T), DeviceStepwiseLog(T)
+    hs, ds = ImportanceSampler(T, hlog, min_counts=2), DeviceImportanceSampler(T, dlog, min_counts=2)
+    g = torch.Generator().manual_seed(0)
+    t, w, ready = ds(5, generator=g)
+    assert not bool(ready) and not hs.is_ready() and t.min() >= 1 and t.max() <= T
+    for rep in range(2):
+        ts = np.arange(1, T + 1)
+        ms = (np.arange(T) + 1.0) * (rep + 1)
+        hlog.update_multiple(ts.tolist(), ms.tolist())
+        dlog.update_multiple(torch.from_numpy(ts), torch.from_numpy(ms))
+    assert hs.is_ready()
+    t, w, ready = ds(4000, generator=g)
+    assert bool(ready)
+    p = hlog.avg_sq_per_step + 1e-6
+    p = p / p.sum()
+    np.testing.assert_allclose(ds.probabilities().numpy(), p, rtol=1e-12)
+    np.testing.assert_allclose(w.numpy(), 1 / (p[t.numpy() - 1] * 4000), rtol=1e-6)  # the reference's weights
+    freq = np.bincount(t.numpy() - 1, minlength=T) / 4000
+    assert np.abs(freq - p).max() < 0.03  # draws follow p
