@@ -33,6 +33,7 @@ struct ConvKArgs {
   int out_H, out_W, out_sh, out_sw, out_oh, out_ow;
   int stages, a_slot_bytes, a_tx_bytes, b_bytes;
   int mt;    // 128-row M sub-tiles per CTA tile sharing one weight tile (1 or 2): 8 UMMAs per barrier round trip
+  int swap;  // 1: operand roles swapped (conv_fwd_swap_kernel): M = 128 output channels, N = 256 pixels
   int nacc;  // accumulator stages in TMEM (2 = epilogue overlaps the next tile's main loop)
   int dbg;   // PDDM_CONV_DBG experiment bits: 1 = empty epilogue, 2 = no A loads, 4 = no MMAs, 8 = no B loads
   uint32_t idesc, layout_type, sbo_bytes, tmem_cols;
@@ -363,6 +364,220 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
+// ------------------------------------------------------------------------------------------------ swapped operands
+// Layers with <= 128 output channels (the 32x32 level of the UNet: 40 % of its conv FLOPs) would run 128x128x16
+// UMMAs, which cost ~105 cycles each against ~144 for 128x256x16 (shared-memory operand reads dominate at N=128).
+// Here the roles are swapped: the WEIGHT tile [128 channels x 64] is the M operand and a tile of 256 PIXELS is the N
+// operand, so every UMMA is 128x256x16.  The accumulator then holds D^T (lane = output channel, column = pixel); the
+// epilogue adds bias + per-sample broadcast per lane, transposes 32x32 blocks through a padded shared-memory stage
+// and finishes pixel-major: residual add from coalesced 16-byte loads, bf16 pack, 16-byte stores.
+// Requirements (checked by the host): Cout <= 128, bf16 output (and residual), identity output map, W a power of two,
+// (pixels per sample in a tile) % 32 == 0.
+constexpr int kSwapPitch = 144;                       // bytes per staged pixel row: 32 fp32 + 16 B pad
+constexpr int kSwapEpiWarps = 8;                      // two warps per TMEM lane quadrant, four pixel chunks each
+constexpr int kSwapThreads = 128 + 32 * kSwapEpiWarps;
+constexpr int kSwapStageBytes = kSwapEpiWarps * 32 * kSwapPitch;  // one 32x32 fp32 block per epilogue warp
+
+__global__ void __launch_bounds__(kSwapThreads, 1)
+conv_fwd_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ ConvKArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kWBytes = 128 * 128;  // weight tile: 128 channels x 64 bf16
+  const int stage_bytes = kWBytes + a.b_bytes;  // + 256 pixels x 64 bf16
+  const int nstages = a.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nstages * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kMaxStages;
+  uint64_t* tmem_full = bars + 2 * kMaxStages;
+  uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  uint8_t* smem_stage = smem + nstages * stage_bytes + 512;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = a.m_tiles;  // pixel tiles (one channel tile)
+  const int total_kb = a.ntaps * a.kblocks_per_tap;
+
+  if (warp == 1 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < nstages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], kSwapEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp >= 1 && warp <= 3) {
+    const int pid = warp - 1;
+    const int kpt = a.kblocks_per_tap, bk = a.bk;
+    const uint32_t tx_bytes = kWBytes + a.a_tx_bytes;  // a_tx_bytes: bytes of the (clipped) pixel box
+    int stage = pid % nstages;
+    uint32_t phase = (pid / nstages) & 1;
+    int kb = pid;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int b0 = (tile / (a.tiles_w * a.tiles_h)) * a.BB;
+      const int h0 = ((tile / a.tiles_w) % a.tiles_h) * a.BH;
+      const int w0 = (tile % a.tiles_w) * a.BW;
+      int tap = kb / kpt, kc = kb - tap * kpt;
+      while (kb < total_kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
+          uint8_t* sw = smem + stage * stage_bytes;
+          mbar_expect_tx(&full_bar[stage], tx_bytes);
+          tma_load_2d(sw, &tmB, &full_bar[stage], (a.tap_w[tap] * kpt + kc) * bk, 0);
+          tma_load_4d(sw + kWBytes, &tmA, &full_bar[stage], kc * bk, w0 + a.tap_dw[tap], h0 + a.tap_dh[tap],
+                      b0 + a.tap_db[tap]);
+        }
+        __syncwarp();
+        kb += kNumProducers;
+        kc += kNumProducers;
+        while (kc >= kpt) {
+          kc -= kpt;
+          ++tap;
+        }
+        stage += kNumProducers;
+        while (stage >= nstages) {
+          stage -= nstages;
+          phase ^= 1;
+        }
+      }
+      kb -= total_kb;
+    }
+  } else if (warp == 0) {
+    const uint64_t desc0 = make_smem_desc(smem_u32(smem), 16, a.sbo_bytes, a.layout_type);
+    const uint32_t stage_d = static_cast<uint32_t>(stage_bytes) >> 4;
+    const uint32_t p_off_d = static_cast<uint32_t>(kWBytes) >> 4;
+    const uint32_t idesc = a.idesc;  // M = 128, N = 256
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * 256;
+      for (int kb = 0; kb < total_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t wdesc = desc0 + static_cast<uint64_t>(stage * stage_d);  // M operand: weights
+          const uint64_t pdesc = wdesc + p_off_d;                                  // N operand: pixels
+          umma_bf16(d_tmem, wdesc, pdesc, idesc, kb != 0);
+          umma_bf16(d_tmem, wdesc + 2, pdesc + 2, idesc, 1);
+          umma_bf16(d_tmem, wdesc + 4, pdesc + 4, idesc, 1);
+          umma_bf16(d_tmem, wdesc + 6, pdesc + 6, idesc, 1);
+          umma_commit(&empty_bar[stage]);
+        }
+        __syncwarp();
+        if (++stage == nstages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (elect_one()) umma_commit(&tmem_full[acc]);
+      __syncwarp();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else {
+    const int q = warp & 3;
+    const int co = q * 32 + lane;  // this thread's output channel (TMEM lane)
+    const int eg = (warp - 4) >> 2;  // which half of the tile's 8 pixel chunks this warp drains
+    uint8_t* stg = smem_stage + (warp - 4) * (32 * kSwapPitch);
+    const int rpb = a.BW * a.BH;   // pixels of one sample inside a tile (multiple of 32)
+    const int wshift = 31 - __clz(a.BW), wmask = a.BW - 1;
+    const bool res = a.residual != nullptr;
+    const float bias_v = (a.bias && co < a.Cout) ? __ldg(a.bias + co) : 0.f;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int tw = tile % a.tiles_w, th = (tile / a.tiles_w) % a.tiles_h, tb = tile / (a.tiles_w * a.tiles_h);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
+      const int c_lo = eg * (8 / (kSwapEpiWarps / 4)), c_hi = c_lo + 8 / (kSwapEpiWarps / 4);
+      uint32_t r[2][32];
+      tmem_ld32(taddr + c_lo * 32, r[0]);
+#pragma unroll 1
+      for (int cp = c_lo; cp < c_hi; cp += 2) {
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          const int c = cp + ci;
+          tmem_ld_wait();
+          if (c + 1 < c_hi) tmem_ld32(taddr + (c + 1) * 32, r[ci ^ 1]);
+          // ---- channel-major part: + bias + per-sample broadcast, park the 32 pixels of this channel
+          const int bs = tb * a.BB + (c * 32) / rpb;  // the 32 pixels of a chunk belong to one sample
+          float add = bias_v;
+          if (a.bcast && co < a.Cout && bs < a.B) add += __ldg(a.bcast + static_cast<size_t>(bs) * a.ld_bcast + co);
+          __syncwarp();  // the previous chunk's pixel-major readers are done with the stage
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            *reinterpret_cast<float*>(stg + j * kSwapPitch + lane * 4) = __uint_as_float(r[ci][j]) + add;
+          __syncwarp();
+          // ---- pixel-major part: lane -> (pixel i*8 + lane/4, 8 channels lane%4), residual, pack, store
+          const int piece = lane & 3;
+          const int n = q * 32 + piece * 8;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int pl = i * 8 + (lane >> 2);
+            const int p = c * 32 + pl;
+            const int bb = p / rpb, rr = p - bb * rpb;
+            const int hh = rr >> wshift, ww = rr & wmask;
+            const int b = tb * a.BB + bb, h = th * a.BH + hh, w = tw * a.BW + ww;
+            const bool valid = (bb < a.BB) && (b < a.B) && (h < a.H) && (w < a.W) && (n < a.Cout);
+            const float4 v0 = *reinterpret_cast<const float4*>(stg + pl * kSwapPitch + piece * 32);
+            const float4 v1 = *reinterpret_cast<const float4*>(stg + pl * kSwapPitch + piece * 32 + 16);
+            if (valid) {
+              float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+              const size_t off = ((static_cast<size_t>(b) * a.H + h) * a.W + w) * a.Cout + n;
+              if (res) {
+                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(
+                    reinterpret_cast<const __nv_bfloat16*>(a.residual) + off));
+                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[k]);
+                  v[2 * k] += __low2float(h2);
+                  v[2 * k + 1] += __high2float(h2);
+                }
+              }
+              uint4 o;
+              o.x = pack_bf16(v[0], v[1]);
+              o.y = pack_bf16(v[2], v[3]);
+              o.z = pack_bf16(v[4], v[5]);
+              o.w = pack_bf16(v[6], v[7]);
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.y) + off) = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 static int pick_block_n(int cout) {
   const int c32 = (cout + 31) / 32 * 32;
   if (c32 <= 256) return c32;
@@ -403,6 +618,80 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
   a.res_dtype = p->res_dtype;
   a.y_dtype = p->y_dtype;
   a.B = p->B; a.H = p->H; a.W = p->W; a.Cout = p->Cout;
+  a.swap = 0;
+  {
+    // swapped-operand path (conv_fwd_swap_kernel): <= 128 output channels on a large pixel count
+    const int PW = p->W < 256 ? p->W : 256;
+    const int PH = 256 / PW < p->H ? 256 / PW : p->H;
+    const int PB = 256 / (PW * PH) < p->B ? 256 / (PW * PH) : p->B;
+    const int tiles = ((p->W + PW - 1) / PW) * ((p->H + PH - 1) / PH) * ((p->B + PB - 1) / PB);
+    const bool pow2w = (p->W & (p->W - 1)) == 0;
+    if (!getenv("PDDM_CONV_NOSWAP") && p->Cout <= 128 && p->Cin % 64 == 0 && p->y_dtype == PDDM_BF16 &&
+        (!p->residual || p->res_dtype == PDDM_BF16) && p->out_sh == 1 && p->out_sw == 1 && p->out_oh == 0 &&
+        p->out_ow == 0 && p->out_H == p->H && p->out_W == p->W && pow2w && PW * PH * PB == 256 &&
+        (PW * PH) % 32 == 0 &&
+        ((tiles >= 2 * device_info().sm_count && p->ntaps * (p->Cin / 64) >= 16) || getenv("PDDM_CONV_SWAP_FORCE"))) {
+      a.swap = 1;
+      a.BW = PW; a.BH = PH; a.BB = PB;
+      a.tiles_w = (p->W + PW - 1) / PW;
+      a.tiles_h = (p->H + PH - 1) / PH;
+      a.m_tiles = tiles;
+      a.n_tiles = 1;
+      a.block_n = 256;
+      a.bk = 64;
+      a.kblocks_per_tap = p->Cin / 64;
+      a.ntaps = p->ntaps;
+      for (int i = 0; i < PDDM_MAX_TAPS; ++i) {
+        a.tap_db[i] = i < p->ntaps ? p->tap_db[i] : 0;
+        a.tap_dh[i] = i < p->ntaps ? p->tap_dh[i] : 0;
+        a.tap_dw[i] = i < p->ntaps ? p->tap_dw[i] : 0;
+        a.tap_w[i] = i < p->ntaps ? p->tap_w[i] : 0;
+        if (i < p->ntaps && (p->tap_w[i] < 0 || p->tap_w[i] >= p->w_ntaps)) return PDDM_ERR_BAD_ARG;
+      }
+      a.out_H = p->out_H; a.out_W = p->out_W; a.out_sh = 1; a.out_sw = 1; a.out_oh = 0; a.out_ow = 0;
+      a.layout_type = kLayoutSW128;
+      a.sbo_bytes = 1024;
+      a.a_slot_bytes = 128 * 128;
+      a.a_tx_bytes = PW * PH * PB * 128;
+      a.b_bytes = 256 * 128;
+      a.idesc = make_idesc_bf16(128, 256, 0, 0);
+      a.mt = 1; a.nacc = 2; a.dbg = 0; a.tmem_cols = 512;
+      const int stage_bytes = 128 * 128 + a.b_bytes;
+      int stages = (device_info().max_smem_optin - 1024 - 512 - kSwapStageBytes) / stage_bytes;
+      if (stages > kMaxStages) stages = kMaxStages;
+      if (stages < 3) return PDDM_ERR_UNSUPPORTED;
+      a.stages = stages;
+      const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 + 512 + kSwapStageBytes;
+      CUtensorMap tmA, tmB;
+      {
+        const uint64_t dims[4] = {static_cast<uint64_t>(p->Cin), static_cast<uint64_t>(p->W),
+                                  static_cast<uint64_t>(p->H), static_cast<uint64_t>(p->x_NB)};
+        const uint64_t str[3] = {static_cast<uint64_t>(p->ldx) * 2, static_cast<uint64_t>(p->W) * p->ldx * 2,
+                                 static_cast<uint64_t>(p->H) * p->W * p->ldx * 2};
+        const uint32_t box[4] = {64, static_cast<uint32_t>(PW), static_cast<uint32_t>(PH), static_cast<uint32_t>(PB)};
+        int rc = make_tmap_bf16(&tmA, p->x, 4, dims, str, box, 128);
+        if (rc) return rc;
+      }
+      {
+        const uint64_t ktot = static_cast<uint64_t>(p->w_ntaps) * p->Cin;
+        const uint64_t dims[2] = {ktot, static_cast<uint64_t>(p->Cout)};
+        const uint64_t str[1] = {ktot * 2};
+        const uint32_t box[2] = {64, 128};
+        int rc = make_tmap_bf16(&tmB, p->w, 2, dims, str, box, 128);
+        if (rc) return rc;
+      }
+      static bool swap_attr_set = false;
+      if (!swap_attr_set) {
+        if (cudaFuncSetAttribute(conv_fwd_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 device_info().max_smem_optin) != cudaSuccess)
+          return PDDM_ERR_CUDA;
+        swap_attr_set = true;
+      }
+      const int grid = tiles < device_info().sm_count ? tiles : device_info().sm_count;
+      PdlLaunch(grid, kSwapThreads, smem_bytes, stream)(conv_fwd_swap_kernel, tmA, tmB, a);
+      return launch_status();
+    }
+  }
   a.BW = p->W < 128 ? p->W : 128;
   a.BH = 128 / a.BW < p->H ? 128 / a.BW : p->H;
   if (a.BH < 1) a.BH = 1;

@@ -271,6 +271,8 @@ int main(int argc, char** argv) {
     add3("3x3 8x8 64->384 b5", 5, 8, 8, 64, 384, 0, 1, -1, PDDM_BF16);
     add3("3x3 4x4 512->256 b20", 20, 4, 4, 512, 256, 1, 1, PDDM_BF16, PDDM_BF16);
     add3("3x3 28x28 32->64 b2", 2, 28, 28, 32, 64, 1, 1, -1, PDDM_BF16);
+    add3("3x3 16x16 128->96 b3 res", 3, 16, 16, 128, 96, 1, 1, PDDM_BF16, PDDM_BF16);  // swap path when forced
+    add3("3x3 8x8 64->128 b9", 9, 8, 8, 64, 128, 1, 0, -1, PDDM_BF16);                   // tile spans 4 samples
     add3("3x3 14x14 96->64 b3", 3, 14, 14, 96, 64, 1, 0, PDDM_BF16, PDDM_F32);
     add3("3x3 7x7 128->64 b5", 5, 7, 7, 128, 64, 1, 0, -1, PDDM_BF16);
     add3("3x3 64x64 128->128 b1", 1, 64, 64, 128, 128, 1, 0, -1, PDDM_BF16);
