@@ -137,7 +137,8 @@ def dominant_kernel_roofline(dev, B, burst_tflops, src):
             # dram__bytes_read+write of one 32x32 128->128 launch from the ncu --set full capture in profiles/
             "traffic": 34.04e6, "traffic_note": "per launch of the 3x3 32x32 128->128 B=128 layer (algorithmic: 67 MB; "
                                                 "the output stays in L2 during the capture)",
-            "kernel": "pddm::conv_fwd_kernel", "launches_timed": int(launches), "us_per_launch": sec / launches * 1e6,
+            "kernel": "pddm::conv_fwd_kernel (conv_fwd_swap_kernel, its swapped-operand variant, for <=128 output channels)",
+            "launches_timed": int(launches), "us_per_launch": sec / launches * 1e6,
             "flops_per_census": flops, "peak_source": f"{src} (burst bf16, kernel timed alone)",
             "workload": "forward 3x3 conv census of the CIFAR UNet at B=128 (62 launches), CUDA events"}
 
