@@ -108,6 +108,17 @@ def avg_pool_nd(dims, *args, **kwargs):
     raise ValueError(f"unsupported dimensions: {dims}")
 
 
+def update_ema(target_params, source_params, rate=0.99):
+    """targ <- rate * targ + (1 - rate) * src over two parameter sequences (src/modules/nn.py:56-66): two multi-tensor
+    launches instead of two launches per tensor."""
+    targs = [t.detach() for t in target_params]
+    srcs = [s.detach() for s in source_params][: len(targs)]
+    targs = targs[: len(srcs)]
+    if targs:
+        torch._foreach_mul_(targs, rate)
+        torch._foreach_add_(targs, srcs, alpha=1 - rate)
+
+
 def zero_module(module):
     """src/modules/nn.py:69-75"""
     for p in module.parameters():

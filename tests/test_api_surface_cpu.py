@@ -71,7 +71,7 @@ def test_unet_and_factories_match_reference():
         missing, mismatched = _check({"__init__": ref_init}, getattr(unet, cls))
         assert not missing and not mismatched, (cls, missing, mismatched)
     ref_nn = _functions(os.path.join(REF, "modules", "nn.py"))
-    missing, mismatched = _check(ref_nn, seam, skip=("update_ema",))
+    missing, mismatched = _check(ref_nn, seam)
     assert not missing, missing
     assert not mismatched, mismatched
     ref_mod = _functions(os.path.join(REF, "modules", "__init__.py"))
