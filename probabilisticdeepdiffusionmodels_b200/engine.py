@@ -552,6 +552,16 @@ class Engine(_Base):
                                   ema_params=self.ema.module.parameters() if fused_ema else None,
                                   ema_decay=self.ema.decay if fused_ema else None)
         st = {"x": torch.zeros(batch_shape, dtype=torch.float32, device=dev), "opt": optimizer}
+        # Learning rate: the captured Adam launch reads it from device memory, so the reference's LR scheduler
+        # (src/engine.py:238-248; Lightning steps it once per epoch) keeps working without re-capturing:
+        # ``step.scheduler_step()`` advances the host-side scheduler and refreshes the device scalars.
+        scheduler = None
+        if hasattr(optimizer, "flush_tables"):  # FusedAdam
+            for g in optimizer.param_groups:
+                g["lr_dev"] = torch.full((1,), float(g["lr"]), dtype=torch.float32, device=dev)
+            if self.scheduler_name:
+                scheduler = getattr(torch.optim.lr_scheduler, self.scheduler_name)(optimizer, **self.scheduler_kwargs)
+        st["scheduler"] = scheduler
         params = [p for p in self.model.parameters() if p.requires_grad]
 
         arena = ops.WeightArena()
@@ -619,5 +629,17 @@ class Engine(_Base):
             graph.replay()
             return st["loss"]
 
+        def sync_lr():
+            for g in optimizer.param_groups:
+                if "lr_dev" in g:
+                    g["lr_dev"].fill_(float(g["lr"]))
+
+        def scheduler_step(*a, **k):
+            if scheduler is not None:
+                scheduler.step(*a, **k)
+            sync_lr()
+
         step.state = st
+        step.sync_lr = sync_lr
+        step.scheduler_step = scheduler_step
         return step

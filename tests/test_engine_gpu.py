@@ -202,3 +202,31 @@ def test_captured_step_with_device_side_loss_log_and_importance_sampler():
     assert float(eng.loss_per_t.avg_sq_per_step.min()) > 0
     # after the switch the loss is the reference's weighted SUM (weights 1/(p_t B)), i.e. of order the mean again
     assert 0 < np.mean(losses[-5:]) < 10 * max(np.mean(losses[:5]), 1e-3) + 10
+
+
+def test_captured_step_follows_the_lr_scheduler_without_recapture():
+    """The captured Adam launch reads the learning rate from device memory: the reference's scheduler configuration
+    (config/scheduler/cosine_annealing.yaml) moves it between replays of the same graph."""
+    eng = make_engine("cosine", log_loss_per_t=False, scheduler_name="CosineAnnealingWarmRestarts",
+                      scheduler_kwargs={"T_0": 4})
+    x = torch.rand(8, 1, 28, 28, device="cuda") * 2 - 1
+    step = eng.capture_train_step(tuple(x.shape))
+    assert step.state["scheduler"] is not None
+    w = eng.model.input_blocks[0][0].weight
+
+    def delta():
+        before = w.detach().clone()
+        step(x)
+        torch.cuda.synchronize()
+        return float((w.detach() - before).abs().max())
+
+    d0 = delta()  # lr = 1e-3: Adam's early steps move a weight by at most ~lr
+    step.scheduler_step()
+    step.scheduler_step()  # cosine restart schedule with T_0 = 4: after 2 epochs lr = lr0 / 2
+    lr_now = step.state["opt"].param_groups[0]["lr"]
+    assert abs(lr_now - 0.5e-3) < 1e-9
+    d1 = delta()
+    assert 0.2 * d0 < d1 < 0.8 * d0, (d0, d1)
+    step.state["opt"].param_groups[0]["lr"] = 0.0
+    step.sync_lr()
+    assert delta() == 0.0
