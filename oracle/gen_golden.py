@@ -146,6 +146,31 @@ def gen_unet():
     np.savez_compressed(os.path.join(GOLD, "unet.npz"), **out)
 
 
+def gen_unet_big():
+    """The headline architectures themselves, batch 1: BASELINE configs[1] (config/model/unet.yaml @32, with and
+    without the learned-variance head) and config/model/unet_celeba.yaml @64.  Output, every parameter's gradient
+    norm, and the small gradients in full (large ones are covered by their norms to keep the fixture small)."""
+    out = {}
+    cases = [("cifar", MODEL_CONFIGS["unet"], 32, 1), ("cifar_sigma", MODEL_CONFIGS["unet"], 32, 2),
+             ("celeba64", MODEL_CONFIGS["unet_celeba"], 64, 1)]
+    for tag, cfg, res, out_mult in cases:
+        m, arch, P = ref_model(cfg, res, seed=11, out_mult=out_mult)
+        x0, t, noise = synth_batch(3, 1, cfg["in_channels"], res, 1000)
+        for p in m.parameters():
+            p.requires_grad_(True)
+        y = m(noise, t)
+        g = torch.from_numpy(np.random.RandomState(5).standard_normal(tuple(y.shape)).astype(np.float32))
+        (y * g).sum().backward()
+        out[f"{tag}_y"] = y.detach().numpy()
+        out[f"{tag}_grad_names"] = np.array([n for n, _ in m.named_parameters()])
+        out[f"{tag}_grad_norms"] = np.array([float(p.grad.double().norm()) for _, p in m.named_parameters()])
+        for n, p in m.named_parameters():
+            if p.numel() <= 4096 and (n.endswith("norm.weight") or n.endswith("in_layers.0.weight") or
+                                      n.startswith("out.") or n.startswith("input_blocks.0.")):
+                out[f"{tag}_grad::{n}"] = p.grad.numpy()
+    np.savez_compressed(os.path.join(GOLD, "unet_big.npz"), **out)
+
+
 def gen_engine():
     """Engine-level: q_sample, loss, one optimiser step, p_sample chains, NLL terms."""
     from src.engine import Engine
@@ -276,6 +301,7 @@ def main():
     gen_schedules()
     gen_kats()
     gen_unet()
+    gen_unet_big()
     gen_engine()
     gen_hybrid()
     for f in sorted(os.listdir(GOLD)):

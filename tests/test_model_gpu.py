@@ -64,6 +64,34 @@ def test_unet_matches_reference_fixture(golden, tag, cfg, res, ls):
             assert rel(got[n].grad, g[key]) < 5e-2, n
 
 
+@pytest.mark.parametrize("tag,name,res,ls", [("cifar", "unet", 32, False), ("cifar_sigma", "unet", 32, True),
+                                             ("celeba64", "unet_celeba", 64, False)])
+def test_headline_architectures_match_reference_fixture(golden, tag, name, res, ls):
+    """BASELINE configs[1] (CIFAR UNet, with / without the learned-variance head) and the CelebA-64 UNet, batch 1,
+    against the unmodified reference's output and gradients (tests/golden/unet_big.npz)."""
+    g = golden["unet_big"]
+    cfg = MODEL_CONFIGS[name]
+    m, arch, P = build(cfg, res, 11, ls)
+    _, t, noise = synth_batch(3, 1, cfg["in_channels"], res, 1000)
+    y = m(noise.cuda(), t.cuda())
+    assert tuple(y.shape) == tuple(g[f"{tag}_y"].shape)
+    assert rel(y, g[f"{tag}_y"]) < 2e-2  # bf16 activations vs the fp32 reference, relative L2
+    gy = torch.from_numpy(np.random.RandomState(5).standard_normal(tuple(y.shape)).astype(np.float32)).cuda()
+    m.zero_grad()
+    (m(noise.cuda(), t.cuda()) * gy).sum().backward()
+    got = dict(m.named_parameters())
+    bad = {}
+    for n, nr in zip(list(g[f"{tag}_grad_names"]), g[f"{tag}_grad_norms"]):
+        if nr > 1e-3:
+            e = abs(float(got[n].grad.double().norm()) - nr) / nr
+            if e > 8e-2:
+                bad[n] = round(e, 4)
+    assert not bad, bad
+    for key in g.files:
+        if key.startswith(f"{tag}_grad::") and float(np.linalg.norm(g[key])) > 1e-3:
+            assert rel(got[key.split("::")[1]].grad, g[key]) < 8e-2, key
+
+
 def test_unet_cifar_config_forward_backward():
     """BASELINE config 2 architecture at B=4 against the oracle run on CPU here."""
     cfg = MODEL_CONFIGS["unet"]

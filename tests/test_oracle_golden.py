@@ -92,6 +92,35 @@ def test_unet_forward_and_grads(golden, tag, cfg, res, out_mult):
             np.testing.assert_allclose(P[n].grad.numpy(), g[key], rtol=2e-3, atol=2e-5 * max(1.0, float(np.abs(g[key]).max())))
 
 
+BIG_CASES = [("cifar", MODEL_CONFIGS["unet"], 32, 1), ("cifar_sigma", MODEL_CONFIGS["unet"], 32, 2),
+             ("celeba64", MODEL_CONFIGS["unet_celeba"], 64, 1)]
+
+
+@pytest.mark.parametrize("tag,cfg,res,out_mult", BIG_CASES)
+def test_unet_headline_architectures_forward_and_grads(golden, tag, cfg, res, out_mult):
+    """The oracle on BASELINE configs[1] (CIFAR UNet) and the CelebA-64 UNet themselves, batch 1, against outputs
+    and gradients of the unmodified reference (tests/golden/unet_big.npz, oracle/gen_golden.py:gen_unet_big)."""
+    g = golden["unet_big"]
+    arch = arch_from_config(res, **{k: v for k, v in cfg.items() if k != "name"}, learn_sigma=(out_mult == 2))
+    P = make_params(arch, seed=11)
+    for p in P.values():
+        p.requires_grad_(True)
+    _, t, noise = synth_batch(3, 1, cfg["in_channels"], res, 1000)
+    y = unet_forward(P, arch, noise, t)
+    np.testing.assert_allclose(y.detach().numpy(), g[f"{tag}_y"], rtol=2e-4, atol=5e-5)
+    gy = T(np.random.RandomState(5).standard_normal(tuple(y.shape)).astype(np.float32))
+    (y * gy).sum().backward()
+    names = list(g[f"{tag}_grad_names"])
+    assert names == list(P.keys())
+    norms = np.array([float(P[n].grad.double().norm()) for n in names])
+    np.testing.assert_allclose(norms, g[f"{tag}_grad_norms"], rtol=5e-4, atol=2e-4)
+    for key in g.files:
+        if key.startswith(f"{tag}_grad::"):
+            n = key.split("::")[1]
+            np.testing.assert_allclose(P[n].grad.numpy(), g[key], rtol=5e-3,
+                                       atol=5e-5 * max(1.0, float(np.abs(g[key]).max())))
+
+
 def test_param_census_matches_survey():
     # SURVEY.md Appendix A
     for name, res, nparams, flops in [("unet_small_grey", 28, 1062497, 373418240), ("unet_small_grey", 32, 1062497, 487915520),
