@@ -205,6 +205,13 @@ typedef struct {
   int32_t B, HW, C, G;
   float eps;
   int32_t silu;
+  /* -- optional extensions (all zero = the plain contiguous single-tensor case) ----------------------------
+   * Row strides in elements (0 = C): x is [B, HW, ldx], y is [B, HW, ldy] -- channel-slice views are allowed.
+   * Two-source input (the concat-free th.cat([h, skip], 1) of src/modules/unet.py:492): channels [0, C_a) are read
+   * from x, channels [C_a, C) from x2[..., 0 : C - C_a] (row stride ldx2).  bf16, no scale/shift only. */
+  const void* x2;
+  int32_t C_a;
+  int32_t ldx, ldx2, ldy;
 } pddm_gn_fwd_params;
 size_t pddm_gn_silu_fwd_workspace(int32_t B, int32_t G);
 int pddm_gn_silu_fwd(const pddm_gn_fwd_params* p, void* workspace, size_t workspace_bytes, pddm_stream_t stream);
@@ -233,7 +240,35 @@ typedef struct {
   float* dshift;
   int32_t B, HW, C, G;
   int32_t silu;
+  /* -- optional extensions (all zero = the plain contiguous single-tensor case; bf16, no scale/shift only) ----
+   * x2/C_a/ldx/ldx2: two-source input as in the forward; lddy: row stride of dy.
+   * gres [B, HW, ld_gres] bf16: a gradient that reaches x by another route (the residual / skip branch,
+   *   src/modules/unet.py:201,234) and is added to dx before it is stored: dx_total = dx_norm + gres.
+   * dx / dx2 receive channels [0, C_a) / [C_a, C) (dx2 = NULL: dx is one [B, HW, ld_dx] tensor of all C channels);
+   *   dx_accumulate / dx2_accumulate: add into the destination (bulk-tensor reduce) instead of overwriting it --
+   *   the fan-in of a tensor that also feeds a later th.cat.
+   * part_dgamma / part_dbeta [B, ld_part] fp32: per-SAMPLE partial sums (the caller reduces them over the batch,
+   *   one launch for a whole network); dgamma / dbeta may then be NULL.
+   * dx_colsum [B, ld_colsum], dx_colsum2 [B, ld_colsum2]: sum_hw dx_total per segment; *_accumulate adds to it. */
+  const void* x2;
+  int32_t C_a;
+  int32_t ldx, ldx2, lddy;
+  const void* gres;
+  int32_t ld_gres;
+  void* dx2;
+  int32_t ld_dx, ld_dx2;
+  int32_t dx_accumulate, dx2_accumulate;
+  float* part_dgamma;
+  float* part_dbeta;
+  int32_t ld_part;
+  float* dx_colsum2;
+  int32_t ld_colsum, ld_colsum2;
+  int32_t colsum_accumulate, colsum2_accumulate;
 } pddm_gn_bwd_params;
+/* > 0 (the number of pipeline slots) if the persistent bulk-tensor GroupNorm kernels take this shape with `ntens`
+ * tensors resident per item (forward: 1; backward: 2, or 3 with gres), 0 if the call would use the older
+ * cluster kernels (which support none of the extensions above). */
+int pddm_gn_pipe_slots(int32_t B, int32_t HW, int32_t C, int32_t G, int32_t C_a, int32_t ntens);
 size_t pddm_gn_silu_bwd_workspace(int32_t B, int32_t C);
 int pddm_gn_silu_bwd(const pddm_gn_bwd_params* p, void* workspace, size_t workspace_bytes, pddm_stream_t stream);
 

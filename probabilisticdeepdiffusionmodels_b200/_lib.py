@@ -50,14 +50,20 @@ class VlbParams(C.Structure):
 class GnFwdParams(C.Structure):
     _fields_ = [("x", c_vp), ("x_dtype", c_i32), ("gamma", c_vp), ("beta", c_vp), ("scale", c_vp), ("shift", c_vp),
                 ("ld_ss", c_i32), ("y", c_vp), ("mean", c_vp), ("rstd", c_vp), ("B", c_i32), ("HW", c_i32),
-                ("C", c_i32), ("G", c_i32), ("eps", c_f32), ("silu", c_i32)]
+                ("C", c_i32), ("G", c_i32), ("eps", c_f32), ("silu", c_i32),
+                ("x2", c_vp), ("C_a", c_i32), ("ldx", c_i32), ("ldx2", c_i32), ("ldy", c_i32)]
 
 
 class GnBwdParams(C.Structure):
     _fields_ = [("x", c_vp), ("x_dtype", c_i32), ("dy", c_vp), ("gamma", c_vp), ("beta", c_vp), ("scale", c_vp),
                 ("shift", c_vp), ("ld_ss", c_i32), ("mean", c_vp), ("rstd", c_vp), ("dx", c_vp), ("dx_dtype", c_i32),
                 ("dgamma", c_vp), ("dbeta", c_vp), ("dx_colsum", c_vp), ("dscale", c_vp), ("dshift", c_vp),
-                ("B", c_i32), ("HW", c_i32), ("C", c_i32), ("G", c_i32), ("silu", c_i32)]
+                ("B", c_i32), ("HW", c_i32), ("C", c_i32), ("G", c_i32), ("silu", c_i32),
+                ("x2", c_vp), ("C_a", c_i32), ("ldx", c_i32), ("ldx2", c_i32), ("lddy", c_i32),
+                ("gres", c_vp), ("ld_gres", c_i32), ("dx2", c_vp), ("ld_dx", c_i32), ("ld_dx2", c_i32),
+                ("dx_accumulate", c_i32), ("dx2_accumulate", c_i32), ("part_dgamma", c_vp), ("part_dbeta", c_vp),
+                ("ld_part", c_i32), ("dx_colsum2", c_vp), ("ld_colsum", c_i32), ("ld_colsum2", c_i32),
+                ("colsum_accumulate", c_i32), ("colsum2_accumulate", c_i32)]
 
 
 class ConvParams(C.Structure):
@@ -133,6 +139,7 @@ SIGNATURES = {
     "pddm_gn_silu_fwd": (c_i32, [P(GnFwdParams), c_vp, c_sz, c_vp]),
     "pddm_gn_silu_bwd_workspace": (c_sz, [c_i32, c_i32]),
     "pddm_gn_silu_bwd": (c_i32, [P(GnBwdParams), c_vp, c_sz, c_vp]),
+    "pddm_gn_pipe_slots": (c_i32, [c_i32, c_i32, c_i32, c_i32, c_i32, c_i32]),
     "pddm_conv2d_fwd": (c_i32, [P(ConvParams), c_vp]),
     "pddm_conv2d_wgrad_workspace": (c_sz, [P(WgradParams)]),
     "pddm_conv2d_wgrad": (c_i32, [P(WgradParams), c_vp, c_sz, c_vp]),

@@ -626,11 +626,11 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
     const int PB = 256 / (PW * PH) < p->B ? 256 / (PW * PH) : p->B;
     const int tiles = ((p->W + PW - 1) / PW) * ((p->H + PH - 1) / PH) * ((p->B + PB - 1) / PB);
     const bool pow2w = (p->W & (p->W - 1)) == 0;
-    if (!getenv("PDDM_CONV_NOSWAP") && p->Cout <= 128 && p->Cin % 64 == 0 && p->y_dtype == PDDM_BF16 &&
+    if (!env_knobs().conv_noswap && p->Cout <= 128 && p->Cin % 64 == 0 && p->y_dtype == PDDM_BF16 &&
         (!p->residual || p->res_dtype == PDDM_BF16) && p->out_sh == 1 && p->out_sw == 1 && p->out_oh == 0 &&
         p->out_ow == 0 && p->out_H == p->H && p->out_W == p->W && pow2w && PW * PH * PB == 256 &&
         (PW * PH) % 32 == 0 &&
-        ((tiles >= 2 * device_info().sm_count && p->ntaps * (p->Cin / 64) >= 16) || getenv("PDDM_CONV_SWAP_FORCE"))) {
+        ((tiles >= 2 * device_info().sm_count && p->ntaps * (p->Cin / 64) >= 16) || env_knobs().conv_swap_force)) {
       a.swap = 1;
       a.BW = PW; a.BH = PH; a.BB = PB;
       a.tiles_w = (p->W + PW - 1) / PW;
@@ -680,13 +680,7 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
         int rc = make_tmap_bf16(&tmB, p->w, 2, dims, str, box, 128);
         if (rc) return rc;
       }
-      static bool swap_attr_set = false;
-      if (!swap_attr_set) {
-        if (cudaFuncSetAttribute(conv_fwd_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 device_info().max_smem_optin) != cudaSuccess)
-          return PDDM_ERR_CUDA;
-        swap_attr_set = true;
-      }
+      if (ensure_smem_optin(reinterpret_cast<const void*>(conv_fwd_swap_kernel))) return PDDM_ERR_CUDA;
       const int grid = tiles < device_info().sm_count ? tiles : device_info().sm_count;
       PdlLaunch(grid, kSwapThreads, smem_bytes, stream)(conv_fwd_swap_kernel, tmA, tmB, a);
       return launch_status();
@@ -730,9 +724,9 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
   // Measured on B200 it does not pay: a 128x128x16 UMMA costs ~105 cycles against ~144 for 128x256x16 whatever the
   // issue pattern, and the 256-row tiles lose more to wave quantisation than they gain.  Kept as an experiment knob.
   a.mt = 1;
-  if (getenv("PDDM_CONV_MT")) a.mt = atoi(getenv("PDDM_CONV_MT")) == 2 && a.block_n <= 128 ? 2 : 1;
+  if (env_knobs().conv_mt == 2 && a.block_n <= 128) a.mt = 2;
   a.nacc = (2 * a.mt * a.block_n <= 512) ? 2 : 1;
-  a.dbg = getenv("PDDM_CONV_DBG") ? atoi(getenv("PDDM_CONV_DBG")) : 0;
+  a.dbg = env_knobs().conv_dbg > 0 ? env_knobs().conv_dbg : 0;
   uint32_t cols = 32;
   while (cols < static_cast<uint32_t>(a.nacc * a.mt * a.block_n)) cols <<= 1;
   a.tmem_cols = cols;
@@ -740,7 +734,7 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
   const int budget = device_info().max_smem_optin - 1024 - 512 - kAddBytes;
   int stages = budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
-  if (getenv("PDDM_CONV_STAGES") && atoi(getenv("PDDM_CONV_STAGES")) < stages) stages = atoi(getenv("PDDM_CONV_STAGES"));
+  if (env_knobs().conv_stages > 0 && env_knobs().conv_stages < stages) stages = env_knobs().conv_stages;
   if (stages < 2) return PDDM_ERR_UNSUPPORTED;
   a.stages = stages;
   const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 + 512 + kAddBytes;
@@ -764,13 +758,7 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
     int rc = make_tmap_bf16(&tmB, p->w, 2, dims, str, box, swz);
     if (rc) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             device_info().max_smem_optin) != cudaSuccess)
-      return PDDM_ERR_CUDA;
-    attr_set = true;
-  }
+  if (ensure_smem_optin(reinterpret_cast<const void*>(conv_fwd_kernel))) return PDDM_ERR_CUDA;
   const int total_tiles = ((a.m_tiles + a.mt - 1) / a.mt) * a.n_tiles;
   const int grid = total_tiles < device_info().sm_count ? total_tiles : device_info().sm_count;
   PdlLaunch(grid, kConvThreads, smem_bytes, stream)(conv_fwd_kernel, tmA, tmB, a);

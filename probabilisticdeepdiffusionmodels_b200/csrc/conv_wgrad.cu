@@ -361,13 +361,7 @@ extern "C" int pddm_conv2d_wgrad(const pddm_wgrad_params* p, void* workspace, si
     rc = make_tmap_bf16(&tmX, p->x, 4, dims, str, box, 128);
     if (rc) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             device_info().max_smem_optin) != cudaSuccess)
-      return PDDM_ERR_CUDA;
-    attr_set = true;
-  }
+  if (ensure_smem_optin(reinterpret_cast<const void*>(conv_wgrad_kernel))) return PDDM_ERR_CUDA;
   PdlLaunch(plan.grid, kWgThreads, plan.smem_bytes, stream)(conv_wgrad_kernel, tmDY, tmX, plan.a);
   if (cudaPeekAtLastError() != cudaSuccess) return PDDM_ERR_CUDA;
   const size_t total = static_cast<size_t>(p->Cout) * p->ntaps * p->Cin;

@@ -684,7 +684,7 @@ static bool make_slab_geom(int B, int HW, int C, int G, int nslabs, int nscratch
   // fastest when a CTA holds about 64 KB of slabs (all of its slabs together): smaller CTAs pay their fixed cost
   // (barriers, folds, cluster exchange) too often, larger ones leave one CTA per SM.  Among the feasible sizes pick
   // the one closest to that; PDDM_GN_S forces an upper bound for experiments.
-  const int smax = getenv("PDDM_GN_S") ? atoi(getenv("PDDM_GN_S")) : 8;
+  const int smax = env_knobs().gn_s > 0 ? env_knobs().gn_s : 8;
   int best_S = 0;
   long long best_dist = 0;
   for (int S = 8; S >= 1; S /= 2) {
@@ -742,6 +742,10 @@ static int make_geom(int B, int HW, int C, int G, GnGeom* g, int* threads) {
   return PDDM_OK;
 }
 
+// groupnorm_pipe.cu
+int gn_fwd_pipe(const pddm_gn_fwd_params* p, cudaStream_t s);
+int gn_bwd_pipe(const pddm_gn_bwd_params* p, float* part_dgamma, float* part_dbeta, int ld_part, cudaStream_t s);
+
 static int launch_cluster(const void* func, dim3 grid, int threads, size_t smem, int S, cudaStream_t s, void** args) {
   PdlLaunch l(grid, dim3(threads), smem, s, S);
   return l.launch_c(func, args) == cudaSuccess ? PDDM_OK : PDDM_ERR_CUDA;
@@ -774,20 +778,20 @@ extern "C" int pddm_gn_silu_fwd(const pddm_gn_fwd_params* p, void* workspace, si
   int rc = make_geom(p->B, p->HW, p->C, p->G, &g, &threads);
   if (rc) return rc;
   if (!aligned16(p->x) || !aligned16(p->y)) return PDDM_ERR_BAD_ARG;
-  if (!p->scale && p->x_dtype == PDDM_BF16 && !getenv("PDDM_GN_STREAM")) {
+  if (!env_knobs().gn_nopipe && !env_knobs().gn_stream) {
+    rc = gn_fwd_pipe(p, s);  // persistent bulk-tensor kernel (groupnorm_pipe.cu); 1 = shape does not qualify
+    if (rc != 1) return rc;
+  }
+  // the cluster kernels below take one contiguous tensor only
+  if (p->x2 || (p->ldx && p->ldx != p->C) || (p->ldy && p->ldy != p->C)) return PDDM_ERR_UNSUPPORTED;
+  if (!p->scale && p->x_dtype == PDDM_BF16 && !env_knobs().gn_stream) {
     SlabGeom sg;
     int st;
     size_t ssm;
     if (make_slab_geom(p->B, p->HW, p->C, p->G, 1, 2, &sg, &st, &ssm)) {
       const void* fn = p->silu ? reinterpret_cast<const void*>(gn_fwd_slab_kernel<true>)
                                : reinterpret_cast<const void*>(gn_fwd_slab_kernel<false>);
-      static bool attr_done[2] = {false, false};
-      if (!attr_done[p->silu ? 1 : 0]) {
-        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, device_info().max_smem_optin) !=
-            cudaSuccess)
-          return PDDM_ERR_CUDA;
-        attr_done[p->silu ? 1 : 0] = true;
-      }
+      if (ensure_smem_optin(fn)) return PDDM_ERR_CUDA;
       pddm_gn_fwd_params pp = *p;
       void* args[2] = {&pp, &sg};
       rc = launch_cluster(fn, dim3(sg.S, sg.B), st, ssm, sg.S, s, args);
@@ -809,9 +813,9 @@ extern "C" int pddm_gn_silu_fwd(const pddm_gn_fwd_params* p, void* workspace, si
 extern "C" int pddm_gn_silu_bwd(const pddm_gn_bwd_params* p, void* workspace, size_t workspace_bytes,
                                 pddm_stream_t s_) {
   cudaStream_t s = static_cast<cudaStream_t>(s_);
-  if (!p || !p->x || !p->dy || !p->dx || !p->gamma || !p->beta || !p->mean || !p->rstd || !p->dgamma || !p->dbeta ||
-      !workspace)
-    return PDDM_ERR_BAD_ARG;
+  if (!p || !p->x || !p->dy || !p->dx || !p->gamma || !p->beta || !p->mean || !p->rstd) return PDDM_ERR_BAD_ARG;
+  if ((!p->dgamma || !p->dbeta) && (!p->part_dgamma || !p->part_dbeta)) return PDDM_ERR_BAD_ARG;
+  if ((p->dgamma || p->dbeta) && !workspace) return PDDM_ERR_BAD_ARG;
   if ((p->scale == nullptr) != (p->shift == nullptr)) return PDDM_ERR_BAD_ARG;
   GnGeom g;
   int threads;
@@ -819,24 +823,40 @@ extern "C" int pddm_gn_silu_bwd(const pddm_gn_bwd_params* p, void* workspace, si
   if (rc) return rc;
   if (!aligned16(p->x) || !aligned16(p->dy) || !aligned16(p->dx)) return PDDM_ERR_BAD_ARG;
   const size_t need = static_cast<size_t>(g.B) * 5 * g.C * sizeof(float);
-  if (workspace_bytes < need) return PDDM_ERR_WORKSPACE;
+  const bool want_final = p->dgamma && p->dbeta;  // else the caller reduces the per-sample partials itself
+  if (want_final && workspace_bytes < need) return PDDM_ERR_WORKSPACE;
   float* tot = static_cast<float*>(workspace);
+  if (!env_knobs().gn_nopipe && !env_knobs().gn_stream) {
+    // persistent bulk-tensor kernel (groupnorm_pipe.cu).  Per-sample partials go to the caller's matrices, or to
+    // tot[b][0][c] (dbeta) / tot[b][1][c] (dgamma), which the batch fold below reads.
+    float* pg = p->part_dgamma ? p->part_dgamma : tot + g.C;
+    float* pb = p->part_dbeta ? p->part_dbeta : tot;
+    const int ldp = p->part_dgamma ? (p->ld_part > 0 ? p->ld_part : g.C) : 5 * g.C;
+    rc = gn_bwd_pipe(p, pg, pb, ldp, s);
+    if (rc == PDDM_OK) {
+      if (want_final) {
+        if (p->part_dgamma) return PDDM_ERR_BAD_ARG;  // either final sums or partials, not both
+        PdlLaunch((g.C + 31) / 32, dim3(32, 32), 0, s)(gn_bwd_finalize_kernel, *p, tot, g);
+      }
+      return launch_status();
+    }
+    if (rc != 1) return rc;
+  }
+  // the cluster kernels below take one contiguous tensor and none of the extensions
+  if (p->x2 || p->gres || p->dx2 || p->part_dgamma || p->dx_colsum2 || p->dx_accumulate || p->colsum_accumulate ||
+      (p->ldx && p->ldx != p->C) || (p->lddy && p->lddy != p->C) || (p->ld_dx && p->ld_dx != p->C) ||
+      (p->ld_colsum && p->ld_colsum != p->C))
+    return PDDM_ERR_UNSUPPORTED;
   const bool ss = p->scale != nullptr;
   bool launched = false;
-  if (!ss && p->x_dtype == PDDM_BF16 && p->dx_dtype == PDDM_BF16 && !getenv("PDDM_GN_STREAM")) {
+  if (!ss && p->x_dtype == PDDM_BF16 && p->dx_dtype == PDDM_BF16 && !env_knobs().gn_stream) {
     SlabGeom sg;
     int st;
     size_t ssm;
     if (make_slab_geom(p->B, p->HW, p->C, p->G, 2, 3, &sg, &st, &ssm)) {
       const void* fn = p->silu ? reinterpret_cast<const void*>(gn_bwd_slab_kernel<true>)
                                : reinterpret_cast<const void*>(gn_bwd_slab_kernel<false>);
-      static bool attr_done[2] = {false, false};
-      if (!attr_done[p->silu ? 1 : 0]) {
-        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, device_info().max_smem_optin) !=
-            cudaSuccess)
-          return PDDM_ERR_CUDA;
-        attr_done[p->silu ? 1 : 0] = true;
-      }
+      if (ensure_smem_optin(fn)) return PDDM_ERR_CUDA;
       pddm_gn_bwd_params pp = *p;
       void* args[3] = {&pp, &tot, &sg};
       rc = launch_cluster(fn, dim3(sg.S, sg.B), st, ssm, sg.S, s, args);

@@ -5,14 +5,35 @@
 
 namespace pddm {
 
-bool pdl_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("PDDM_PDL");
-    v = (e && e[0] == '1') ? 1 : 0;  // opt-in: measured neutral inside CUDA graphs (17.0 vs 16.8 ms/step)
-  }
-  return v == 1;
+static int env_int(const char* name) {
+  const char* e = getenv(name);
+  return (e && e[0]) ? atoi(e) : -1;
 }
+static int env_set(const char* name) { return getenv(name) ? 1 : 0; }
+
+const EnvKnobs& env_knobs() {
+  static EnvKnobs k;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    k.pdl = env_int("PDDM_PDL");
+    k.conv_noswap = env_set("PDDM_CONV_NOSWAP");
+    k.conv_swap_force = env_set("PDDM_CONV_SWAP_FORCE");
+    k.conv_mt = env_int("PDDM_CONV_MT");
+    k.conv_dbg = env_int("PDDM_CONV_DBG");
+    k.conv_stages = env_int("PDDM_CONV_STAGES");
+    k.gn_stream = env_set("PDDM_GN_STREAM");
+    k.gn_nopipe = env_set("PDDM_GN_NOPIPE");
+    k.gn_s = env_int("PDDM_GN_S");
+    k.gn_dbg = env_int("PDDM_GN_DBG");
+    k.gn_cc = env_int("PDDM_GN_CC");
+    k.gn_ng = env_int("PDDM_GN_NG");
+    k.attn_dbg = env_int("PDDM_ATTN_DBG");
+  });
+  return k;
+}
+
+// opt-in: measured neutral inside CUDA graphs (17.0 vs 16.8 ms/step)
+bool pdl_enabled() { return env_knobs().pdl == 1; }
 
 
 const DeviceInfo& device_info() {
@@ -38,6 +59,26 @@ const DeviceInfo& device_info() {
     have[dev] = true;
   }
   return info[dev];
+}
+
+int ensure_smem_optin(const void* fn) {
+  static std::mutex mu;
+  static const void* seen_fn[256];
+  static int seen_dev[256];
+  static int nseen = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return PDDM_ERR_CUDA;
+  std::lock_guard<std::mutex> lock(mu);
+  for (int i = 0; i < nseen; ++i)
+    if (seen_fn[i] == fn && seen_dev[i] == dev) return PDDM_OK;
+  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, device_info().max_smem_optin) != cudaSuccess)
+    return PDDM_ERR_CUDA;
+  if (nseen < 256) {
+    seen_fn[nseen] = fn;
+    seen_dev[nseen] = dev;
+    ++nseen;
+  }
+  return PDDM_OK;
 }
 
 EncodeTiledFn encode_tiled_fn() {

@@ -17,6 +17,30 @@ struct DeviceInfo {
 };
 const DeviceInfo& device_info();
 
+// Experiment knobs (environment variables), read ONCE per process -- the launch paths themselves are stateless
+// and never call getenv.  -1 = not set.
+struct EnvKnobs {
+  int pdl;              // PDDM_PDL=1: programmatic dependent launch
+  int conv_noswap;      // PDDM_CONV_NOSWAP: never use the swapped-operand conv kernel
+  int conv_swap_force;  // PDDM_CONV_SWAP_FORCE: use it whenever the shape allows
+  int conv_mt;          // PDDM_CONV_MT
+  int conv_dbg;         // PDDM_CONV_DBG bit mask
+  int conv_stages;      // PDDM_CONV_STAGES upper bound
+  int gn_stream;        // PDDM_GN_STREAM: register-streaming GroupNorm kernels only
+  int gn_nopipe;        // PDDM_GN_NOPIPE: skip the persistent bulk-tensor GroupNorm kernels
+  int gn_s;             // PDDM_GN_S: upper bound on the GroupNorm cluster size
+  int gn_dbg;           // PDDM_GN_DBG experiment bit mask (groupnorm_pipe.cu)
+  int gn_ng;            // PDDM_GN_NG=1: one compute group instead of two in the persistent GroupNorm kernels
+  int gn_cc;            // PDDM_GN_CC: force the channel-chunk width of the persistent GroupNorm kernels
+  int attn_dbg;         // PDDM_ATTN_DBG
+};
+const EnvKnobs& env_knobs();
+
+// Opt `fn` in to the device's maximum dynamic shared memory.  The attribute is per (device, function); it is set on
+// first use and remembered in a mutex-protected cache (like device_info), so launch paths stay re-entrant and work
+// with several devices in one process.  Returns PDDM_OK or PDDM_ERR_CUDA.
+int ensure_smem_optin(const void* fn);
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

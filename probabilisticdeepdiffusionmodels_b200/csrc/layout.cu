@@ -516,13 +516,7 @@ static int colsum_launch(const void* x, int ld, long long rows_per_seg, int segs
   const size_t smem = static_cast<size_t>(g.nlanes) * C * sizeof(float);
   if (g.gx > 1 && (!ws || ws_bytes < static_cast<size_t>(segs) * g.gx * C * sizeof(float))) return PDDM_ERR_WORKSPACE;
   if (smem > 48 * 1024) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      if (cudaFuncSetAttribute(colsum_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) !=
-          cudaSuccess)
-        return PDDM_ERR_CUDA;
-      attr_set = true;
-    }
+    if (ensure_smem_optin(reinterpret_cast<const void*>(colsum_partial_kernel))) return PDDM_ERR_CUDA;
     if (smem > 64 * 1024) return PDDM_ERR_UNSUPPORTED;
   }
   PdlLaunch(dim3(g.gx, segs), g.threads, smem, s)(colsum_partial_kernel, static_cast<const bf16*>(x), ld, rows_per_seg,
@@ -567,12 +561,7 @@ extern "C" int pddm_pack_weights_multi(const void* descs, const void* blocks, in
   if (!descs || !blocks || nblocks <= 0 || max_ntaps <= 0 || max_ntaps > PDDM_MAX_TAPS) return PDDM_ERR_BAD_ARG;
   const size_t smem = static_cast<size_t>(kPackTile) * (kPackTile * max_ntaps + 1) * sizeof(float);
   if (smem > 48 * 1024) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      if (cudaFuncSetAttribute(pack_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess)
-        return PDDM_ERR_CUDA;
-      attr_set = true;
-    }
+    if (ensure_smem_optin(reinterpret_cast<const void*>(pack_multi_kernel))) return PDDM_ERR_CUDA;
     if (smem > 96 * 1024) return PDDM_ERR_UNSUPPORTED;
   }
   PdlLaunch(nblocks, 256, smem, S(s))(pack_multi_kernel, static_cast<const PackDesc*>(descs),

@@ -280,18 +280,41 @@ def timestep_embedding(t, dim, max_period=10000, dtype=bf16):
 
 
 # ------------------------------------------------------------------------------------------ group norm
-def gn_silu_fwd(x, gamma, beta, groups=32, eps=1e-5, silu=True, scale=None, shift=None):
-    """x: [B, ..., C] bf16/fp32 -> (y bf16, mean [B,G], rstd [B,G])."""
+def _ld(t, what="tensor"):
+    """Row stride (elements) of a [B, ..., C] activation that may be a channel-slice view of a wider NHWC tensor."""
+    if not t.is_cuda:
+        raise RuntimeError("pddm_b200 ops need CUDA tensors (sm_100a); there is no CPU fallback")
+    if t.stride(-1) != 1:
+        raise RuntimeError(f"{what}: channels must be innermost")
+    ld = t.stride(-2) if t.dim() >= 2 else t.shape[-1]
+    for i in range(t.dim() - 2):
+        if t.shape[i] != 1 and t.stride(i) != t.stride(i + 1) * t.shape[i + 1]:
+            raise RuntimeError(f"{what}: only channel-slice views of a contiguous NHWC tensor are supported")
+    return int(ld)
+
+
+def gn_pipe_slots(B, HW, C, groups, C_a=0, ntens=1):
+    """> 0 if the persistent bulk-tensor GroupNorm kernel takes this shape (ntens: 1 fwd, 2 bwd, 3 bwd with gres)."""
+    return int(L.load().pddm_gn_pipe_slots(B, HW, C, groups, C_a, ntens))
+
+
+def gn_silu_fwd(x, gamma, beta, groups=32, eps=1e-5, silu=True, scale=None, shift=None, x2=None, out=None):
+    """x: [B, ..., C_a] bf16/fp32 (+ optional second source x2 [B, ..., C - C_a]: the concat-free th.cat of
+    src/modules/unet.py:492) -> (y bf16 [B, ..., C], mean [B,G], rstd [B,G])."""
     L.require_device(x)
-    _chk(x)
-    B, C_ = x.shape[0], x.shape[-1]
-    HW = x.numel() // (B * C_)
-    y = torch.empty(x.shape, dtype=bf16, device=x.device)
+    B, C_a = x.shape[0], x.shape[-1]
+    C_ = C_a + (x2.shape[-1] if x2 is not None else 0)
+    HW = x.numel() // (B * C_a)
+    y = out if out is not None else torch.empty(x.shape[:-1] + (C_,), dtype=bf16, device=x.device)
     mean = torch.empty((B, groups), dtype=f32, device=x.device)
     rstd = torch.empty((B, groups), dtype=f32, device=x.device)
     p = L.GnFwdParams()
     p.x, p.x_dtype, p.gamma, p.beta, p.y, p.mean, p.rstd = L.ptr(x), L.dt(x), L.ptr(gamma), L.ptr(beta), L.ptr(y), \
         L.ptr(mean), L.ptr(rstd)
+    p.ldx, p.ldy = _ld(x, "x"), _ld(y, "y")
+    if x2 is not None:
+        assert x2.dtype == x.dtype and x2.shape[:-1] == x.shape[:-1]
+        p.x2, p.C_a, p.ldx2 = L.ptr(x2), C_a, _ld(x2, "x2")
     if scale is not None:
         p.scale, p.shift, p.ld_ss = L.ptr(scale), L.ptr(shift), scale.stride(0)
     p.B, p.HW, p.C, p.G, p.eps, p.silu = B, HW, C_, groups, eps, 1 if silu else 0
@@ -301,37 +324,69 @@ def gn_silu_fwd(x, gamma, beta, groups=32, eps=1e-5, silu=True, scale=None, shif
 
 
 def gn_silu_bwd(x, dy, gamma, beta, mean, rstd, groups=32, silu=True, scale=None, shift=None, dx_dtype=bf16,
-                want_colsum=False):
-    """-> dx, dgamma, dbeta, dx_colsum [B,C] | None, dscale, dshift"""
-    _chk(x)
-    _chk(dy, bf16)
-    B, C_ = x.shape[0], x.shape[-1]
-    HW = x.numel() // (B * C_)
+                want_colsum=False, x2=None, gres=None, dx=None, dx2=None, dx_accumulate=False, dx2_accumulate=False,
+                part_dgamma=None, part_dbeta=None, colsum=None, colsum2=None, colsum_accumulate=False,
+                colsum2_accumulate=False):
+    """-> dx, dgamma, dbeta, dx_colsum [B,C] | None, dscale, dshift.
+
+    Extensions of the persistent kernel (bf16, no scale-shift; see include/pddm.h): ``x2`` second source, ``gres`` a
+    gradient added to dx on the way out, ``dx`` / ``dx2`` caller-provided destinations for channels [0, C_a) /
+    [C_a, C) (dx alone: one tensor of all C channels), ``*_accumulate`` add into the destination, ``part_dgamma`` /
+    ``part_dbeta`` [B, >=C] per-sample partial sums instead of the batch-reduced dgamma / dbeta (returned as None),
+    ``colsum`` / ``colsum2`` destinations of sum_hw dx per segment."""
+    L.require_device(x)
+    if dy.dtype != bf16:
+        raise TypeError(f"expected {bf16}, got {dy.dtype}")
+    B, C_a = x.shape[0], x.shape[-1]
+    C_ = C_a + (x2.shape[-1] if x2 is not None else 0)
+    HW = x.numel() // (B * C_a)
     dev = x.device
-    dx = torch.empty(x.shape, dtype=dx_dtype, device=dev)
-    dgamma = torch.empty(C_, dtype=f32, device=dev)
-    dbeta = torch.empty(C_, dtype=f32, device=dev)
-    colsum_ = torch.empty((B, C_), dtype=f32, device=dev) if want_colsum else None
+    if dx is None:
+        if x2 is not None and dx2 is None:
+            dx2 = torch.empty(x2.shape, dtype=dx_dtype, device=dev)
+        dx = torch.empty(x.shape if dx2 is not None else x.shape[:-1] + (C_,), dtype=dx_dtype, device=dev)
+    partials = part_dgamma is not None
+    dgamma = dbeta = None
+    if not partials:
+        dgamma = torch.empty(C_, dtype=f32, device=dev)
+        dbeta = torch.empty(C_, dtype=f32, device=dev)
+    if colsum is None and want_colsum:
+        colsum = torch.empty((B, C_a if colsum2 is not None else C_), dtype=f32, device=dev)
     dscale = dshift = None
     p = L.GnBwdParams()
     p.x, p.x_dtype, p.dy, p.gamma, p.beta, p.mean, p.rstd = L.ptr(x), L.dt(x), L.ptr(dy), L.ptr(gamma), L.ptr(beta), \
         L.ptr(mean), L.ptr(rstd)
+    p.ldx, p.lddy, p.ld_dx = _ld(x, "x"), _ld(dy, "dy"), _ld(dx, "dx")
+    if x2 is not None:
+        p.x2, p.C_a, p.ldx2 = L.ptr(x2), C_a, _ld(x2, "x2")
+    if gres is not None:
+        assert gres.dtype == bf16 and gres.shape[-1] == C_
+        p.gres, p.ld_gres = L.ptr(gres), _ld(gres, "gres")
+    if dx2 is not None:
+        p.dx2, p.ld_dx2 = L.ptr(dx2), _ld(dx2, "dx2")
+    p.dx_accumulate, p.dx2_accumulate = int(bool(dx_accumulate)), int(bool(dx2_accumulate))
+    if partials:
+        assert part_dbeta is not None and part_dgamma.stride(0) == part_dbeta.stride(0)
+        p.part_dgamma, p.part_dbeta, p.ld_part = L.ptr(part_dgamma), L.ptr(part_dbeta), part_dgamma.stride(0)
     if scale is not None:
         dscale = torch.empty((B, C_), dtype=f32, device=dev)
         dshift = torch.empty((B, C_), dtype=f32, device=dev)
         p.scale, p.shift, p.ld_ss = L.ptr(scale), L.ptr(shift), scale.stride(0)
-        assert scale.stride(0) == C_ or True
         # dscale/dshift are written with the same leading dimension as scale/shift
         if scale.stride(0) != C_:
             dscale = torch.empty((B, scale.stride(0)), dtype=f32, device=dev)
             dshift = torch.empty((B, scale.stride(0)), dtype=f32, device=dev)
         p.dscale, p.dshift = L.ptr(dscale), L.ptr(dshift)
     p.dx, p.dx_dtype, p.dgamma, p.dbeta = L.ptr(dx), L.dt(dx), L.ptr(dgamma), L.ptr(dbeta)
-    p.dx_colsum = L.ptr(colsum_)
+    if colsum is not None:
+        p.dx_colsum, p.ld_colsum = L.ptr(colsum), colsum.stride(0)
+    if colsum2 is not None:
+        p.dx_colsum2, p.ld_colsum2 = L.ptr(colsum2), colsum2.stride(0)
+    p.colsum_accumulate, p.colsum2_accumulate = int(bool(colsum_accumulate)), int(bool(colsum2_accumulate))
     p.B, p.HW, p.C, p.G, p.silu = B, HW, C_, groups, 1 if silu else 0
-    ws = _ws(L.load().pddm_gn_silu_bwd_workspace(B, C_), dev)
-    L.call("pddm_gn_silu_bwd", C.byref(p), L.ptr(ws), C.c_size_t(ws.numel()), L.stream())
-    return dx, dgamma, dbeta, colsum_, dscale, dshift
+    ws = _ws(L.load().pddm_gn_silu_bwd_workspace(B, C_), dev) if not partials else None
+    L.call("pddm_gn_silu_bwd", C.byref(p), L.ptr(ws), C.c_size_t(ws.numel() if ws is not None else 0), L.stream())
+    return (dx if dx2 is None else (dx, dx2)), dgamma, dbeta, colsum, dscale, dshift
 
 
 # ------------------------------------------------------------------------------------------ attention

@@ -57,8 +57,17 @@ def main():
         n = B * HW * C
         tot_f += tf
         tot_b += tb
-        print(f"B={B} HW={HW:5d} C={C:4d}  fwd {tf:7.1f} us {4 * n / tf * 1e-3:7.0f} GB/s   "
-              f"bwd {tb:7.1f} us {6 * n / tb * 1e-3:7.0f} GB/s", flush=True)
+        extra = ""
+        if F.gn_pipe_slots(B, HW, C, 32, 0, 3) >= 2 and not os.environ.get("PDDM_GN_NOPIPE"):
+            # backward with the residual-branch gradient fused in (8 B/element) and per-sample partial sums
+            pg = torch.empty(B, C, device=dev)
+            pb = torch.empty(B, C, device=dev)
+            tg = timed(lambda i: F.gn_silu_bwd(xs[i], dys[i], gamma, beta, mean, rstd, want_colsum=True,
+                                               gres=dys[(i + 1) % nbuf], part_dgamma=pg, part_dbeta=pb), nbuf)
+            extra = f"   bwd+gres {tg:7.1f} us {8 * n / tg * 1e-3:7.0f} GB/s"
+        print(f"B={B} HW={HW:5d} C={C:4d}  slots {F.gn_pipe_slots(B, HW, C, 32, 0, 1)}/{F.gn_pipe_slots(B, HW, C, 32, 0, 2)}"
+              f"  fwd {tf:7.1f} us {4 * n / tf * 1e-3:7.0f} GB/s   "
+              f"bwd {tb:7.1f} us {6 * n / tb * 1e-3:7.0f} GB/s{extra}", flush=True)
     print(f"sum fwd {tot_f:.1f} us, bwd {tot_b:.1f} us")
 
 
