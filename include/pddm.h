@@ -303,6 +303,11 @@ typedef struct {
   int32_t tap_w[PDDM_MAX_TAPS]; /* weight slot read by each tap: w[n, tap_w[tap], c]; w has w_ntaps slots per row */
   int32_t w_ntaps;
   int32_t out_H, out_W, out_sh, out_sw, out_oh, out_ow;
+  /* optional second source (concat-free th.cat([h, skip], 1), src/modules/unet.py:492): input channels [0, Cin_a) are
+   * read from x, channels [Cin_a, Cin) from x2[..., 0 : Cin - Cin_a] (same [x_NB, H, W] extents, row stride ldx2).
+   * Cin_a must be a multiple of the K-block (64, or 32 when Cin % 64 != 0).  NULL = single source. */
+  const void* x2;
+  int32_t Cin_a, ldx2;
 } pddm_conv_params;
 int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream);
 
@@ -319,6 +324,9 @@ typedef struct {
   int32_t tap_db[PDDM_MAX_TAPS], tap_dh[PDDM_MAX_TAPS], tap_dw[PDDM_MAX_TAPS];
   int32_t dw_layout;
   int32_t accumulate; /* dw += instead of dw = */
+  /* layout 1 only: dw is the channel slice [dw_c0, dw_c0 + Cin) of a parameter with dw_ldc input channels
+   * (the two halves of a conv whose input is a two-source concat); 0 = the whole parameter (dw_ldc = Cin). */
+  int32_t dw_ldc, dw_c0;
 } pddm_wgrad_params;
 size_t pddm_conv2d_wgrad_workspace(const pddm_wgrad_params* p);
 int pddm_conv2d_wgrad(const pddm_wgrad_params* p, void* workspace, size_t workspace_bytes, pddm_stream_t stream);
@@ -340,11 +348,26 @@ typedef struct {
   const float* src;
   void* dst; /* bf16 */
   int32_t Cout, Cin, ntaps, mode, Cout_pad, Cin_pad;
+  int32_t ld_dst;   /* elements between consecutive destination rows; 0 = dense (ntaps * Cin_pad | ntaps * Cout_pad):
+                       lets several parameters be packed side by side into one wide GEMM operand */
+  int32_t reserved;
 } pddm_pack_desc;
 int pddm_pack_weights_multi(const void* descs, const void* blocks, int32_t nblocks, int32_t max_ntaps,
                             pddm_stream_t stream);
 /* out[c] = sum_m x[m, c] for a small fp32 matrix [M, C] (deterministic). */
 int pddm_colsum_f32(const float* x, int32_t M, int32_t C, float* out, pddm_stream_t stream);
+/* Per-sample column sums with strides: out[b, c] (+)= sum_hw x[b, hw, c] for x bf16 [B, HW, ldx] (c < C),
+ * out fp32 [B, ld_out]; one launch, fixed summation order.  (bias gradients, src/modules/unet.py:102,219) */
+int pddm_colsum_rows(const void* x, int32_t ldx, int32_t B, int32_t HW, int32_t C, float* out, int32_t ld_out,
+                     int32_t accumulate, pddm_stream_t stream);
+/* Batch fold of a matrix of per-sample partial sums: dst[j] = sum_b ps[b, src_of[j]] for j < n (src_of = NULL:
+ * identity), fixed order.  ONE launch turns every per-sample partial of a backward pass (GroupNorm dgamma / dbeta,
+ * bias column sums) into parameter gradients. */
+int pddm_batch_fold(const float* ps, int32_t ld, int32_t B, const int32_t* src_of, int32_t n, float* dst,
+                    pddm_stream_t stream);
+/* dst[r, c] = (bf16) src[r, c] for strided row-major matrices (rows x cols, cols % 8 == 0, 16-byte aligned rows). */
+int pddm_convert_rows(const float* src, int32_t ld_src, void* dst, int32_t ld_dst, int32_t rows, int32_t cols,
+                      pddm_stream_t stream);
 
 /* Helpers that put the two "thin" convolutions on the tensor cores as well: the stem conv (Cin <= 4, reads the
  * NCHW fp32 model input, src/modules/unet.py:353) becomes a K=32 GEMM over an im2col patch matrix, and the head conv

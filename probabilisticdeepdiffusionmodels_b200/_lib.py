@@ -74,7 +74,7 @@ class ConvParams(C.Structure):
                 ("tap_db", c_i32 * MAX_TAPS), ("tap_dh", c_i32 * MAX_TAPS), ("tap_dw", c_i32 * MAX_TAPS),
                 ("tap_w", c_i32 * MAX_TAPS), ("w_ntaps", c_i32),
                 ("out_H", c_i32), ("out_W", c_i32), ("out_sh", c_i32), ("out_sw", c_i32), ("out_oh", c_i32),
-                ("out_ow", c_i32)]
+                ("out_ow", c_i32), ("x2", c_vp), ("Cin_a", c_i32), ("ldx2", c_i32)]
 
 
 class WgradParams(C.Structure):
@@ -82,12 +82,12 @@ class WgradParams(C.Structure):
                 ("x_NB", c_i32), ("B", c_i32), ("H", c_i32), ("W", c_i32), ("Cin", c_i32), ("ldx", c_i32),
                 ("Cout", c_i32), ("lddy", c_i32), ("ntaps", c_i32),
                 ("tap_db", c_i32 * MAX_TAPS), ("tap_dh", c_i32 * MAX_TAPS), ("tap_dw", c_i32 * MAX_TAPS),
-                ("dw_layout", c_i32), ("accumulate", c_i32)]
+                ("dw_layout", c_i32), ("accumulate", c_i32), ("dw_ldc", c_i32), ("dw_c0", c_i32)]
 
 
 class PackDesc(C.Structure):
     _fields_ = [("src", c_vp), ("dst", c_vp), ("Cout", c_i32), ("Cin", c_i32), ("ntaps", c_i32), ("mode", c_i32),
-                ("Cout_pad", c_i32), ("Cin_pad", c_i32)]
+                ("Cout_pad", c_i32), ("Cin_pad", c_i32), ("ld_dst", c_i32), ("reserved", c_i32)]
 
 
 PACK_TILE = 32  # PDDM_PACK_TILE
@@ -146,6 +146,9 @@ SIGNATURES = {
     "pddm_pack_conv_weight": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "pddm_pack_weights_multi": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp]),
     "pddm_colsum_f32": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp]),
+    "pddm_colsum_rows": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp]),
+    "pddm_batch_fold": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp]),
+    "pddm_convert_rows": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_vp]),
     "pddm_im2col3x3": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "pddm_nchw_to_nhwc_padded": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "pddm_nhwc_slice_to_nchw": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),

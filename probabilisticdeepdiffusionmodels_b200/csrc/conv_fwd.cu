@@ -32,6 +32,7 @@ struct ConvKArgs {
   int tap_db[PDDM_MAX_TAPS], tap_dh[PDDM_MAX_TAPS], tap_dw[PDDM_MAX_TAPS], tap_w[PDDM_MAX_TAPS];
   int out_H, out_W, out_sh, out_sw, out_oh, out_ow;
   int stages, a_slot_bytes, a_tx_bytes, b_bytes;
+  int kc_split;  // K-blocks [kc_split, kblocks_per_tap) of every tap are read from the second source tensor
   int mt;    // 128-row M sub-tiles per CTA tile sharing one weight tile (1 or 2): 8 UMMAs per barrier round trip
   int swap;  // 1: operand roles swapped (conv_fwd_swap_kernel): M = 128 output channels, N = 256 pixels
   int nacc;  // accumulator stages in TMEM (2 = epilogue overlaps the next tile's main loop)
@@ -46,8 +47,8 @@ constexpr int kMaxAddRows = 8;                   // tile rows may span up to thi
 constexpr int kAddBytes = kMaxAddRows * 256 * 4;  // smem for the staged bias + per-sample broadcast vector
 
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ ConvKArgs a) {
+conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvKArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int mt = a.mt;
@@ -69,6 +70,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   if (warp == 1 && lane == 0) {
     tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmB);
   }
   if (warp == 0 && lane == 0) {
@@ -125,10 +127,13 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           uint8_t* sa = smem + stage * stage_bytes;
           mbar_expect_tx(&full_bar[stage], tx_bytes);
           if (!(dbg & 2)) {
-            tma_load_4d(sa, &tmA, &full_bar[stage], kc * bk, w0 + a.tap_dw[tap], h0 + a.tap_dh[tap],
-                        b0 + a.tap_db[tap]);
+            // two-source input (concat-free skip connection): the trailing K-blocks of a tap come from tmA2
+            const bool second = kc >= a.kc_split;
+            const CUtensorMap* ma = second ? &tmA2 : &tmA;
+            const int ck = (second ? kc - a.kc_split : kc) * bk;
+            tma_load_4d(sa, ma, &full_bar[stage], ck, w0 + a.tap_dw[tap], h0 + a.tap_dh[tap], b0 + a.tap_db[tap]);
             if (mt == 2)
-              tma_load_4d(sa + a_slot, &tmA, &full_bar[stage], kc * bk, w1 + a.tap_dw[tap], h1 + a.tap_dh[tap],
+              tma_load_4d(sa + a_slot, ma, &full_bar[stage], ck, w1 + a.tap_dw[tap], h1 + a.tap_dh[tap],
                           b1 + a.tap_db[tap]);
           }
           if (!(dbg & 8))
@@ -604,7 +609,15 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
   if (p->B <= 0 || p->H <= 0 || p->W <= 0 || p->Cin <= 0 || p->Cout <= 0 || p->ntaps <= 0 ||
       p->ntaps > PDDM_MAX_TAPS || p->x_NB < p->B || p->w_ntaps < 1 || p->w_ntaps > PDDM_MAX_TAPS)
     return PDDM_ERR_BAD_ARG;
-  if (p->Cin % 32 != 0 || p->Cout % 8 != 0 || p->ldx % 8 != 0 || p->ldx < p->Cin) return PDDM_ERR_UNSUPPORTED;
+  if (p->Cin % 32 != 0 || p->Cout % 8 != 0 || p->ldx % 8 != 0) return PDDM_ERR_UNSUPPORTED;
+  if (p->x2) {
+    const int kb = (p->Cin % 64 == 0) ? 64 : 32;
+    if (p->Cin_a <= 0 || p->Cin_a >= p->Cin || p->Cin_a % kb != 0 || p->ldx < p->Cin_a || p->ldx2 % 8 != 0 ||
+        p->ldx2 < p->Cin - p->Cin_a || !aligned16(p->x2))
+      return PDDM_ERR_UNSUPPORTED;
+  } else if (p->ldx < p->Cin) {
+    return PDDM_ERR_UNSUPPORTED;
+  }
   if (!aligned16(p->x) || !aligned16(p->w) || !aligned16(p->y) || (p->residual && !aligned16(p->residual)) ||
       (p->bias && !aligned16(p->bias)) || (p->bcast && (!aligned16(p->bcast) || p->ld_bcast % 4 != 0)))
     return PDDM_ERR_BAD_ARG;
@@ -626,7 +639,7 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
     const int PB = 256 / (PW * PH) < p->B ? 256 / (PW * PH) : p->B;
     const int tiles = ((p->W + PW - 1) / PW) * ((p->H + PH - 1) / PH) * ((p->B + PB - 1) / PB);
     const bool pow2w = (p->W & (p->W - 1)) == 0;
-    if (!env_knobs().conv_noswap && p->Cout <= 128 && p->Cin % 64 == 0 && p->y_dtype == PDDM_BF16 &&
+    if (!env_knobs().conv_noswap && !p->x2 && p->Cout <= 128 && p->Cin % 64 == 0 && p->y_dtype == PDDM_BF16 &&
         (!p->residual || p->res_dtype == PDDM_BF16) && p->out_sh == 1 && p->out_sw == 1 && p->out_oh == 0 &&
         p->out_ow == 0 && p->out_H == p->H && p->out_W == p->W && pow2w && PW * PH * PB == 256 &&
         (PW * PH) % 32 == 0 &&
@@ -739,9 +752,11 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
   a.stages = stages;
   const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 + 512 + kAddBytes;
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmA2, tmB;
+  const int cin_a = p->x2 ? p->Cin_a : p->Cin;
+  a.kc_split = cin_a / a.bk;
   {
-    const uint64_t dims[4] = {static_cast<uint64_t>(p->Cin), static_cast<uint64_t>(p->W), static_cast<uint64_t>(p->H),
+    const uint64_t dims[4] = {static_cast<uint64_t>(cin_a), static_cast<uint64_t>(p->W), static_cast<uint64_t>(p->H),
                               static_cast<uint64_t>(p->x_NB)};
     const uint64_t str[3] = {static_cast<uint64_t>(p->ldx) * 2, static_cast<uint64_t>(p->W) * p->ldx * 2,
                              static_cast<uint64_t>(p->H) * p->W * p->ldx * 2};
@@ -749,6 +764,14 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
                              static_cast<uint32_t>(a.BB)};
     int rc = make_tmap_bf16(&tmA, p->x, 4, dims, str, box, swz);
     if (rc) return rc;
+    tmA2 = tmA;
+    if (p->x2) {
+      const uint64_t dims2[4] = {static_cast<uint64_t>(p->Cin - cin_a), dims[1], dims[2], dims[3]};
+      const uint64_t str2[3] = {static_cast<uint64_t>(p->ldx2) * 2, static_cast<uint64_t>(p->W) * p->ldx2 * 2,
+                                static_cast<uint64_t>(p->H) * p->W * p->ldx2 * 2};
+      rc = make_tmap_bf16(&tmA2, p->x2, 4, dims2, str2, box, swz);
+      if (rc) return rc;
+    }
   }
   {
     const uint64_t ktot = static_cast<uint64_t>(p->w_ntaps) * p->Cin;
@@ -761,6 +784,6 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
   if (ensure_smem_optin(reinterpret_cast<const void*>(conv_fwd_kernel))) return PDDM_ERR_CUDA;
   const int total_tiles = ((a.m_tiles + a.mt - 1) / a.mt) * a.n_tiles;
   const int grid = total_tiles < device_info().sm_count ? total_tiles : device_info().sm_count;
-  PdlLaunch(grid, kConvThreads, smem_bytes, stream)(conv_fwd_kernel, tmA, tmB, a);
+  PdlLaunch(grid, kConvThreads, smem_bytes, stream)(conv_fwd_kernel, tmA, tmA2, tmB, a);
   return launch_status();
 }

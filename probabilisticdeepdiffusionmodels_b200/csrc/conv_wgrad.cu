@@ -222,7 +222,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
 
 // dw[layout] (+)= sum_s partial[s][n][tap][c]   (fixed summation order: deterministic; 4 channels per thread)
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int Cout,
-                                    int ntaps, int Cin, int layout, int accumulate) {
+                                    int ntaps, int Cin, int layout, int accumulate, int ldc, int c0) {
   pdl_entry();
   const size_t total4 = static_cast<size_t>(Cout) * ntaps * Cin / 4;
   for (size_t i4 = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i4 < total4;
@@ -248,7 +248,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
       const int c = static_cast<int>(i % Cin);
       const int tap = static_cast<int>((i / Cin) % ntaps);
       const int n = static_cast<int>(i / (static_cast<size_t>(Cin) * ntaps));
-      float* o = dw + (static_cast<size_t>(n) * Cin + c) * ntaps + tap;
+      float* o = dw + (static_cast<size_t>(n) * ldc + c0 + c) * ntaps + tap;
       const float v[4] = {s.x, s.y, s.z, s.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) o[j * ntaps] = accumulate ? o[j * ntaps] + v[j] : v[j];
@@ -368,7 +368,9 @@ extern "C" int pddm_conv2d_wgrad(const pddm_wgrad_params* p, void* workspace, si
   int blocks = static_cast<int>((total / 4 + 255) / 256);
   if (blocks > 2368) blocks = 2368;
   if (blocks < 1) blocks = 1;
+  if (p->dw_ldc && (p->dw_layout != 1 || p->dw_c0 < 0 || p->dw_c0 + p->Cin > p->dw_ldc)) return PDDM_ERR_BAD_ARG;
   PdlLaunch(blocks, 256, 0, stream)(wgrad_reduce_kernel, plan.a.partial, p->dw, plan.a.splits, p->Cout, p->ntaps, p->Cin,
-                                                  p->dw_layout, p->accumulate);
+                                    p->dw_layout, p->accumulate, p->dw_ldc ? p->dw_ldc : p->Cin,
+                                    p->dw_ldc ? p->dw_c0 : 0);
   return launch_status();
 }

@@ -275,6 +275,7 @@ struct PackDesc {
   const float* src;
   bf16* dst;
   int Cout, Cin, ntaps, mode, Cout_p, Cin_p;
+  int ld_dst, reserved;  // ld_dst: elements between destination rows (0 = dense)
 };
 constexpr int kPackTile = 32;
 __global__ void __launch_bounds__(256) pack_multi_kernel(const PackDesc* __restrict__ descs,
@@ -306,13 +307,15 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const PackDesc* __restr
       if (co >= d.Cout_p || ci >= d.Cin_p) continue;
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = tile[r * pitch + (piece * 8 + j) * nt + tap];
-      dst_off = (static_cast<long long>(co) * nt + tap) * d.Cin_p + ci;
+      dst_off = d.ld_dst ? static_cast<long long>(co) * d.ld_dst + tap * d.Cin_p + ci
+                         : (static_cast<long long>(co) * nt + tap) * d.Cin_p + ci;
     } else {  // dst[ci][ntaps-1-tap][co]: r = input channel, piece = 8 output channels
       const int ci = ci0 + r, co = co0 + piece * 8;
       if (ci >= d.Cin_p || co >= d.Cout_p) continue;
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = tile[(piece * 8 + j) * pitch + r * nt + tap];
-      dst_off = (static_cast<long long>(ci) * nt + (nt - 1 - tap)) * d.Cout_p + co;
+      dst_off = d.ld_dst ? static_cast<long long>(ci) * d.ld_dst + (nt - 1 - tap) * d.Cout_p + co
+                         : (static_cast<long long>(ci) * nt + (nt - 1 - tap)) * d.Cout_p + co;
     }
     *reinterpret_cast<uint4*>(d.dst + dst_off) = pack8(v);
   }
@@ -331,6 +334,76 @@ __global__ void colsum_f32_kernel(const float* __restrict__ x, int M, int C, flo
 #pragma unroll
     for (int k = 1; k < 8; ++k) a += sh[k][threadIdx.x];
     out[c] = a;
+  }
+}
+
+// out[b, c] (+)= sum_hw x[b, hw, c]: grid (ceil(C/64), B), 256 threads = 32 row lanes x 8 units of 8 channels
+__global__ void __launch_bounds__(256) colsum_rows_kernel(const bf16* __restrict__ x, int ldx, int HW, int C,
+                                                          float* __restrict__ out, int ld_out, int accumulate) {
+  pdl_entry();
+  __shared__ float sh[32][65];
+  const int b = blockIdx.y, c0 = blockIdx.x * 64;
+  const int u = threadIdx.x & 7, lane = threadIdx.x >> 3;
+  const int c = c0 + u * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c < C) {
+    const bf16* xp = x + (static_cast<size_t>(b) * HW) * ldx + c;
+    for (int r = lane; r < HW; r += 128) {
+      uint4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (r + 32 * k < HW) v[k] = *reinterpret_cast<const uint4*>(xp + static_cast<size_t>(r + 32 * k) * ldx);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (r + 32 * k < HW) {
+          float f[8];
+          unpack8(v[k], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[lane][u * 8 + j] = acc[j];
+  __syncthreads();
+  if (threadIdx.x < 64 && c0 + threadIdx.x < C) {
+    float v = 0.f;
+#pragma unroll 8
+    for (int l = 0; l < 32; ++l) v += sh[l][threadIdx.x];
+    float* o = out + static_cast<size_t>(b) * ld_out + c0 + threadIdx.x;
+    *o = accumulate ? *o + v : v;
+  }
+}
+// dst[j] = sum_b ps[b, src_of[j]] (fixed order, 8 loads in flight per thread)
+__global__ void batch_fold_kernel(const float* __restrict__ ps, int ld, int B, const int* __restrict__ src_of, int n,
+                                  float* __restrict__ dst) {
+  pdl_entry();
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int col = src_of ? src_of[j] : j;
+  const float* p = ps + col;
+  float s = 0.f;
+  int b = 0;
+  for (; b + 8 <= B; b += 8) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __ldg(p + static_cast<size_t>(b + k) * ld);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += v[k];
+  }
+  for (; b < B; ++b) s += __ldg(p + static_cast<size_t>(b) * ld);
+  dst[j] = s;
+}
+__global__ void convert_rows_kernel(const float* __restrict__ src, int ld_src, bf16* __restrict__ dst, int ld_dst,
+                                    int rows, int cols8) {
+  pdl_entry();
+  const long long n = static_cast<long long>(rows) * cols8;
+  GRID_STRIDE(i, n) {
+    const int r = static_cast<int>(i / cols8), c = static_cast<int>(i % cols8) * 8;
+    const float4 a = *reinterpret_cast<const float4*>(src + static_cast<size_t>(r) * ld_src + c);
+    const float4 b = *reinterpret_cast<const float4*>(src + static_cast<size_t>(r) * ld_src + c + 4);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    *reinterpret_cast<uint4*>(dst + static_cast<size_t>(r) * ld_dst + c) = pack8(v);
   }
 }
 
@@ -571,6 +644,28 @@ extern "C" int pddm_pack_weights_multi(const void* descs, const void* blocks, in
 extern "C" int pddm_colsum_f32(const float* x, int32_t M, int32_t C, float* out, pddm_stream_t s) {
   if (!x || !out || M <= 0 || C <= 0) return PDDM_ERR_BAD_ARG;
   PdlLaunch((C + 31) / 32, dim3(32, 8), 0, S(s))(colsum_f32_kernel, x, M, C, out);
+  return launch_status();
+}
+extern "C" int pddm_colsum_rows(const void* x, int32_t ldx, int32_t B, int32_t HW, int32_t C, float* out,
+                                int32_t ld_out, int32_t accumulate, pddm_stream_t s) {
+  if (!x || !out || B <= 0 || HW <= 0 || C <= 0 || ldx < C || ld_out < C) return PDDM_ERR_BAD_ARG;
+  if (C % 8 || ldx % 8 || !aligned16(x)) return PDDM_ERR_UNSUPPORTED;
+  PdlLaunch(dim3((C + 63) / 64, B), 256, 0, S(s))(colsum_rows_kernel, static_cast<const bf16*>(x), ldx, HW, C, out,
+                                                  ld_out, accumulate);
+  return launch_status();
+}
+extern "C" int pddm_batch_fold(const float* ps, int32_t ld, int32_t B, const int32_t* src_of, int32_t n, float* dst,
+                               pddm_stream_t s) {
+  if (!ps || !dst || ld <= 0 || B <= 0 || n <= 0) return PDDM_ERR_BAD_ARG;
+  PdlLaunch((n + 127) / 128, 128, 0, S(s))(batch_fold_kernel, ps, ld, B, src_of, n, dst);
+  return launch_status();
+}
+extern "C" int pddm_convert_rows(const float* src, int32_t ld_src, void* dst, int32_t ld_dst, int32_t rows,
+                                 int32_t cols, pddm_stream_t s) {
+  if (!src || !dst || rows <= 0 || cols <= 0 || ld_src < cols || ld_dst < cols) return PDDM_ERR_BAD_ARG;
+  if (cols % 8 || ld_src % 4 || ld_dst % 8 || !aligned16(src) || !aligned16(dst)) return PDDM_ERR_UNSUPPORTED;
+  PdlLaunch(grid_for(static_cast<long long>(rows) * (cols / 8), 256), 256, 0, S(s))(
+      convert_rows_kernel, src, ld_src, static_cast<bf16*>(dst), ld_dst, rows, cols / 8);
   return launch_status();
 }
 extern "C" int pddm_im2col3x3(const float* x_nchw, void* out, int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t Kp,

@@ -10,7 +10,7 @@ the FID tooling drive it unchanged.  What changed underneath:
 * the reverse chain replays ONE CUDA graph per step (UNet forward + p_sample + step bookkeeping) whose step
   index lives in device memory; the per-step noise still comes from ``torch.randn(generator=...)`` so a seed
   produces the same stream as the reference on the same device;
-* ``fit_step`` / ``capture_train_step`` run forward + backward + Adam (+EMA) as one CUDA graph.
+* ``capture_train_step`` runs forward + backward + Adam (+EMA) as one CUDA graph.
 
 Extensions (off by default = reference behaviour): ``learn_sigma`` (variance channels + L_hybrid, SURVEY.md
 Appendix C) and ``log_loss_per_t=False`` (skips the reference's per-step device->host sync in ``get_loss``).
@@ -101,6 +101,7 @@ class Engine(_Base):
         else:
             self.loss_per_t = StepwiseLog(diffusion_steps, 10)
             self.loss_per_t_epoch = StepwiseLog(diffusion_steps)
+        self.sampling_name = sampling
         if sampling == "uniform":
             self.sampler = UniformSampler(diffusion_steps=diffusion_steps)
         elif sampling == "importance" and log_loss_per_t == "device":
@@ -317,11 +318,25 @@ class Engine(_Base):
         return x_t
 
     # ------------------------------------------------------------------ graph-replayed reverse chain
+    def _weights_stamp(self):
+        """Changes whenever the current model's weights may have changed (in-place torch ops bump ``_version``;
+        kernels that write parameters through raw pointers bump the global epochs)."""
+        from . import plan as _plan
+        return (tuple(p._version for p in self.model.parameters()), ops._EPOCH[0], _plan._EPOCH[0])
+
     def _chain_graph(self, shape, dtype, device, mean_only):
+        """One captured reverse step.  The graph must never read stale weights (optimizer steps, EMA updates and
+        ``load_state_dict`` between two sampling calls are the normal case): with a plan, the graph reads its bf16
+        operands from the plan's persistent arena, which ``_chain`` refreshes (one launch) before replaying; on the
+        op-by-op path the graph hard-codes the addresses of cached packs, so it is re-captured when the stamp moves."""
+        from . import plan as _plan
         key = (tuple(shape), str(device), bool(mean_only), id(self.model), self.clip_while_generating,
                self.sigma_mode, self.learn_sigma)
         g = self._chain_graphs.get(key)
-        if g is not None:
+        probe = torch.empty(shape, dtype=torch.float32, device=device)
+        pl = _plan.plan_for(self.model, probe)
+        stamp = None if pl is not None else self._weights_stamp()
+        if g is not None and g["plan"] is pl and (pl is not None or g["stamp"] == stamp):
             return g
         st = {"x": torch.zeros(shape, dtype=torch.float32, device=device),
               "z": None if mean_only else torch.zeros(shape, dtype=torch.float32, device=device),
@@ -350,6 +365,7 @@ class Engine(_Base):
         with torch.cuda.graph(graph):
             step()
         st["graph"] = graph
+        st["plan"], st["stamp"] = pl, stamp
         self._chain_graphs[key] = st
         return st
 
@@ -360,6 +376,8 @@ class Engine(_Base):
         snaps, stds = [], []
         with ops.frozen_weights():
             st = self._chain_graph(x_t.shape, x_t.dtype, x_t.device, mean_only)
+            if st["plan"] is not None:
+                st["plan"].refresh_packs()  # the replayed graph reads the arena: make it current (one launch)
             st["x"].copy_(x_t)
             st["t_dev"].fill_(int(t_start))
             st["t_vec"].fill_(float(t_start))
@@ -536,6 +554,20 @@ class Engine(_Base):
         per = self.per_sample_loss(self.model(x_t, t), noise, x, x_t, t)
         return (torch.sum(weights * per) if weights is not None else torch.mean(per)), per
 
+    def loss_and_grad(self, model_out, noise, x, x_t, t, gscale):
+        """Per-sample training loss (L_simple, or L_hybrid with learned variance -- SURVEY.md App. C.6) and the gradient
+        of ``sum_b gscale[b] * loss[b]`` w.r.t. the model output, from the fused loss kernels (no autograd)."""
+        model_out, noise = model_out.contiguous(), noise.contiguous()
+        if self.learn_sigma:
+            w = self.diffusion_steps / 1000.0
+            per_simple, _ = F.sq_err(model_out, noise)
+            vb, gv = F.vlb_terms(x.contiguous(), x_t.contiguous(), model_out, t, self.tabs(x.device), mode=1,
+                                 want_grad_v=True)
+            _, dout = F.sq_err(model_out, noise, gscale, want_grad=True, grad_v_unit=gv, v_scale=w)
+            return per_simple + w * vb, dout
+        per, dout = F.sq_err(model_out, noise, gscale, want_grad=True)
+        return per, dout
+
     def capture_train_step(self, batch_shape, optimizer=None, grad_hook=None, overlap_wgrad=True):
         """Capture one optimisation step (t ~ U{1..T}, eps ~ N(0,1) drawn inside the graph, loss, backward,
         optional ``grad_hook`` (e.g. the data-parallel all-reduce), Adam, EMA) as a CUDA graph.
@@ -563,61 +595,122 @@ class Engine(_Base):
                 scheduler = getattr(torch.optim.lr_scheduler, self.scheduler_name)(optimizer, **self.scheduler_kwargs)
         st["scheduler"] = scheduler
         params = [p for p in self.model.parameters() if p.requires_grad]
-
-        arena = ops.WeightArena()
-
         device_log = self.log_loss_per_t == "device"
+        if self.sampling_name == "importance" and not device_log:
+            raise ValueError(
+                'capture_train_step draws timesteps inside the CUDA graph: sampling="importance" needs '
+                'Engine(log_loss_per_t="device") (the host-side loss log cannot be updated from a replayed graph)')
+        from . import _lib, plan as _plan
+        plan = _plan.plan_for(self.model, st["x"]) if all(p.requires_grad for p in self.model.parameters()) else None
+        st["plan"] = plan
+        B = batch_shape[0]
 
-        def fwd_bwd():
+        def draw():
             noise = torch.randn_like(st["x"])
-            if device_log:  # timestep draw (uniform or importance), loss weighting and loss log all inside the graph
-                t, weights, ready = self._draw_timesteps(batch_shape[0])
-                x_t = self.get_q_t(st["x"], noise, t)
-                per = self.per_sample_loss(self.model(x_t, t), noise, st["x"], x_t, t)
+            if device_log:  # timestep draw (uniform or importance) inside the graph
+                t, weights, ready = self._draw_timesteps(B)
+            else:
+                t, weights, ready = torch.randint(1, self.diffusion_steps + 1, (B,), device=dev), None, None
+            return noise, t, weights, ready
+
+        def log_losses(t, per):
+            if device_log:
                 for log in (self.loss_per_t, self.loss_per_t_epoch):
                     if log.device != per.device:
                         log.to(per.device)
                     log.update_multiple(t, per.detach())
-                loss = torch.mean(per) if ready is None else \
-                    torch.where(ready, torch.sum(weights * per), torch.mean(per).to(weights.dtype))
-            else:
-                t = torch.randint(1, self.diffusion_steps + 1, (batch_shape[0],), device=dev)
-                loss, per = self.loss_on(st["x"], t, noise)
-            if overlap_wgrad:
-                with ops.overlap_wgrad():  # weight-gradient GEMMs on a side stream, joined before the optimiser
+
+        def reduce_loss(per, weights, ready):
+            if weights is None:
+                return torch.mean(per)
+            if ready is None:
+                return torch.sum(weights * per)
+            return torch.where(ready, torch.sum(weights * per), torch.mean(per).to(weights.dtype))
+
+        if plan is not None:
+            # ---- hand-scheduled step (plan.py): no autograd, gradients born in one flat arena
+            # (kept in `st`: the graph reads it on every replay, long after this function's locals are gone)
+            uniform_scale = st["uniform_scale"] = torch.full((B,), 1.0 / B, dtype=torch.float32, device=dev)
+
+            def body():
+                plan.repack()  # one launch refreshes every bf16 GEMM operand from the fp32 masters
+                noise, t, weights, ready = draw()
+                x_t = self.get_q_t(st["x"], noise, t)
+                out, S = plan.forward(x_t, t, save=True)
+                if weights is None:
+                    gscale = uniform_scale
+                elif ready is None:
+                    gscale = weights.float()
+                else:
+                    gscale = torch.where(ready, weights.float(), uniform_scale)
+                per, dout = self.loss_and_grad(out, noise, st["x"], x_t, t, gscale)
+                log_losses(t, per)
+                loss = reduce_loss(per, weights, ready)
+                plan.backward(S, dout, overlap=overlap_wgrad)
+                plan.assign_grads()
+                if grad_hook is not None:
+                    grad_hook(plan if getattr(grad_hook, "takes_plan", False) else params)
+                optimizer.step()
+                _plan.bump_weight_epoch()
+                if self.ema is not None and not fused_ema:
+                    self.ema.update(self.model)
+                return loss.detach(), per.detach(), t
+
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side), torch.no_grad():
+                for _ in range(3):
+                    body()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            k0 = _lib.KERNELS[0]
+            with torch.no_grad(), torch.cuda.graph(graph):
+                st["loss"], st["per"], st["t"] = body()
+        else:
+            arena = ops.WeightArena()
+
+            def fwd_bwd():
+                noise, t, weights, ready = draw()
+                x_t = self.get_q_t(st["x"], noise, t)
+                per = self.per_sample_loss(self.model(x_t, t), noise, st["x"], x_t, t)
+                log_losses(t, per)
+                loss = reduce_loss(per, weights, ready)
+                if overlap_wgrad:
+                    with ops.overlap_wgrad():  # weight-gradient GEMMs on a side stream, joined before the optimiser
+                        loss.backward()
+                else:
                     loss.backward()
-            else:
-                loss.backward()
-            return loss, per, t
+                return loss, per, t
 
-        def body():
-            arena.repack()  # one launch refreshes every bf16 weight pack from the fp32 masters
-            with arena.active():
-                loss, per, t = fwd_bwd()
-            if grad_hook is not None:
-                grad_hook(params)
-            optimizer.step()
-            if self.ema is not None and not fused_ema:
-                self.ema.update(self.model)
-            return loss.detach(), per.detach(), t
+            def body():
+                arena.repack()  # one launch refreshes every bf16 weight pack from the fp32 masters
+                with arena.active():
+                    loss, per, t = fwd_bwd()
+                if grad_hook is not None:
+                    grad_hook(params)
+                optimizer.step()
+                _plan.bump_weight_epoch()
+                ops.invalidate_weight_cache()
+                if self.ema is not None and not fused_ema:
+                    self.ema.update(self.model)
+                return loss.detach(), per.detach(), t
 
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            with arena.recording():  # learn which packs the model asks for (forward and backward)
-                fwd_bwd()
-            arena.finalize(dev)
-            st["arena"] = arena
-            for _ in range(3):
-                optimizer.zero_grad(set_to_none=True)
-                body()
-        torch.cuda.current_stream(dev).wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        optimizer.zero_grad(set_to_none=True)
-        from . import _lib
-        k0 = _lib.KERNELS[0]
-        with torch.cuda.graph(graph):
-            st["loss"], st["per"], st["t"] = body()
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                with arena.recording():  # learn which packs the model asks for (forward and backward)
+                    fwd_bwd()
+                arena.finalize(dev)
+                st["arena"] = arena
+                for _ in range(3):
+                    optimizer.zero_grad(set_to_none=True)
+                    body()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            optimizer.zero_grad(set_to_none=True)
+            k0 = _lib.KERNELS[0]
+            with torch.cuda.graph(graph):
+                st["loss"], st["per"], st["t"] = body()
         if hasattr(optimizer, "flush_tables"):
             optimizer.flush_tables()  # pointer tables recorded during capture (gradient addresses of the graph pool)
         st["kernels_per_step"] = _lib.KERNELS[0] - k0  # kernels of this library captured in one step
@@ -627,6 +720,7 @@ class Engine(_Base):
         def step(x):
             st["x"].copy_(x, non_blocking=True)
             graph.replay()
+            _plan.bump_weight_epoch()  # the replayed optimiser kernel changed the weights through raw pointers
             return st["loss"]
 
         def sync_lr():

@@ -86,14 +86,17 @@ def pack_weight(w, mode, cout_pad=None, cin_pad=None):
 
 
 def tap_gemm(x, wp, taps, B, H, W, *, bias=None, bcast=None, residual=None, out=None, out_dtype=bf16,
-             out_hw=None, out_map=(1, 1, 0, 0), cin=None):
+             out_hw=None, out_map=(1, 1, 0, 0), cin=None, x2=None):
     """y[b, oh, ow, :] = sum_taps x[b+db, h+dh, w+dw, :] @ wp[:, slot, :]^T (+bias +bcast[b] +residual).
 
-    x: bf16 [NB, H, W, ldx] (cin <= ldx leading channels used); wp: bf16 [Cout, slots, cin]."""
+    x: bf16 [NB, H, W, ldx] (cin <= ldx leading channels used; channel-slice views allowed); wp: bf16
+    [Cout, slots, cin].  ``x2`` (bf16 [NB, H, W, c2]): second source -- the GEMM's input channels are
+    [x[..., :cin - c2] | x2] without materialising the concat (src/modules/unet.py:492)."""
     L.require_device(x)
-    _chk(x, bf16)
+    if x.dtype != bf16 or wp.dtype != bf16:
+        raise TypeError("tap_gemm operands must be bf16")
     _chk(wp, bf16)
-    NB, ldx = x.shape[0], x.shape[-1]
+    NB, ldx = x.shape[0], _ld(x, "x")
     cout, slots, wcin = wp.shape
     cin = wcin if cin is None else cin
     assert wcin == cin and x.shape[1] == H and x.shape[2] == W
@@ -102,6 +105,9 @@ def tap_gemm(x, wp, taps, B, H, W, *, bias=None, bcast=None, residual=None, out=
         out = torch.empty((B, oH, oW, cout), dtype=out_dtype, device=x.device)
     p = L.ConvParams()
     p.x, p.w, p.y = L.ptr(x), L.ptr(wp), L.ptr(out)
+    if x2 is not None:
+        assert x2.dtype == bf16 and x2.shape[:3] == x.shape[:3] and x.shape[-1] + x2.shape[-1] == cin
+        p.x2, p.Cin_a, p.ldx2 = L.ptr(x2), x.shape[-1], _ld(x2, "x2")
     p.bias = L.ptr(_chk(bias, f32)) if bias is not None else None
     if bcast is not None:  # [B, Cout] fp32, rows may be strided (column slice of a wider matrix)
         assert bcast.dtype == f32 and bcast.is_cuda and bcast.stride(-1) == 1 and bcast.shape[-1] == cout
@@ -120,23 +126,40 @@ def tap_gemm(x, wp, taps, B, H, W, *, bias=None, bcast=None, residual=None, out=
     return out
 
 
-def tap_wgrad(x, dy, taps, B, H, W, cin, cout, w_shape, accumulate_into=None, launch_stream=None, keep=None):
+def wgrad_workspace_bytes(B, H, W, cin, cout, ntaps, x_NB=None):
+    """Bytes of split-K workspace ``tap_wgrad`` needs for this shape (host-side query, no launch)."""
+    p = L.WgradParams()
+    p.x_NB, p.B, p.H, p.W, p.Cin, p.ldx, p.Cout, p.lddy = x_NB or B, B, H, W, cin, cin, cout, cout
+    p.ntaps = ntaps
+    return int(L.load().pddm_conv2d_wgrad_workspace(C.byref(p)))
+
+
+def tap_wgrad(x, dy, taps, B, H, W, cin, cout, w_shape, accumulate_into=None, launch_stream=None, keep=None,
+              out=None, ws=None, dw_ldc=0, dw_c0=0):
     """dw[n, c, tap] = sum_pixels dy[b,h,w,n] * x[b+db, h+dh, w+dw, c]  -> fp32 tensor of shape w_shape.
 
     ``launch_stream``: enqueue on that stream instead of the current one (buffers are still allocated from the
-    current stream's pool; the caller keeps them alive through ``keep`` until it has joined the streams)."""
+    current stream's pool; the caller keeps them alive through ``keep`` until it has joined the streams).
+    ``out``: write the gradient there (a parameter-shaped fp32 tensor, e.g. a slice of a flat gradient arena);
+    with ``dw_ldc`` / ``dw_c0`` it is the input-channel slice [dw_c0, dw_c0 + cin) of a parameter with dw_ldc input
+    channels.  ``ws``: caller-owned split-K workspace (uint8)."""
     L.require_device(x)
-    _chk(x, bf16)
-    _chk(dy, bf16)
-    dw = accumulate_into if accumulate_into is not None else torch.empty(w_shape, dtype=f32, device=x.device)
+    if x.dtype != bf16 or dy.dtype != bf16:
+        raise TypeError("tap_wgrad operands must be bf16")
+    dw = out if out is not None else (accumulate_into if accumulate_into is not None
+                                      else torch.empty(w_shape, dtype=f32, device=x.device))
     p = L.WgradParams()
     p.x, p.dy, p.dw = L.ptr(x), L.ptr(dy), L.ptr(dw)
-    p.x_NB, p.B, p.H, p.W, p.Cin, p.ldx, p.Cout, p.lddy = x.shape[0], B, H, W, cin, x.shape[-1], cout, dy.shape[-1]
+    p.x_NB, p.B, p.H, p.W, p.Cin, p.ldx, p.Cout, p.lddy = x.shape[0], B, H, W, cin, _ld(x, "x"), cout, _ld(dy, "dy")
     _fill_taps(p, taps)
     p.dw_layout = 1
     p.accumulate = 1 if accumulate_into is not None else 0
+    p.dw_ldc, p.dw_c0 = dw_ldc, dw_c0
     nbytes = L.load().pddm_conv2d_wgrad_workspace(C.byref(p))
-    ws = _ws(nbytes, x.device)
+    if ws is None:
+        ws = _ws(nbytes, x.device)
+    elif ws.numel() < nbytes:
+        raise RuntimeError(f"tap_wgrad: workspace of {ws.numel()} bytes, {nbytes} needed")
     st = L.stream() if launch_stream is None else C.c_void_p(launch_stream.cuda_stream)
     L.call("pddm_conv2d_wgrad", C.byref(p), L.ptr(ws), C.c_size_t(ws.numel()), st)
     if keep is not None:
@@ -145,10 +168,34 @@ def tap_wgrad(x, dy, taps, B, H, W, cin, cout, w_shape, accumulate_into=None, la
     return dw
 
 
-def colsum(x2d_bf16, C_):
+def colsum_rows(x, out, accumulate=False):
+    """out[b, c] (+)= sum_hw x[b, hw, c]  (x bf16 [B, ..., C] or a channel-slice view; out fp32 [B, >=C] view)."""
+    if x.dtype != bf16 or out.dtype != f32:
+        raise TypeError("colsum_rows: bf16 in, fp32 out")
+    B, C_ = x.shape[0], x.shape[-1]
+    L.call("pddm_colsum_rows", L.ptr(x), _ld(x, "x"), B, x.numel() // (B * C_), C_, L.ptr(out), out.stride(0),
+           1 if accumulate else 0, L.stream())
+    return out
+
+
+def batch_fold(ps, src_of, n, dst):
+    """dst[j] = sum_b ps[b, src_of[j]], j < n (ps fp32 [B, ld]; src_of int32 device tensor or None = identity)."""
+    L.call("pddm_batch_fold", L.ptr(ps), ps.stride(0), ps.shape[0], L.ptr(src_of), n, L.ptr(dst), L.stream())
+    return dst
+
+
+def convert_rows(src, dst):
+    """dst (bf16 [rows, cols]) = src (fp32 [rows, cols]), either may be a column-slice view of a wider matrix."""
+    assert src.dtype == f32 and dst.dtype == bf16 and src.shape == dst.shape and src.dim() == 2
+    L.call("pddm_convert_rows", L.ptr(src), src.stride(0), L.ptr(dst), dst.stride(0), src.shape[0], src.shape[1],
+           L.stream())
+    return dst
+
+
+def colsum(x2d_bf16, C_, out=None):
     """sum over all leading dims of a bf16 [..., C] tensor -> fp32 [C]."""
     _chk(x2d_bf16, bf16)
-    out = torch.empty(C_, dtype=f32, device=x2d_bf16.device)
+    out = torch.empty(C_, dtype=f32, device=x2d_bf16.device) if out is None else out
     M = x2d_bf16.numel() // x2d_bf16.shape[-1]
     ws = _ws(L.load().pddm_colsum_workspace(C.c_int64(M), 1, C_), x2d_bf16.device)
     L.call("pddm_colsum", L.ptr(x2d_bf16), x2d_bf16.shape[-1], C.c_int64(M), C_, L.ptr(out), 0, L.ptr(ws),

@@ -107,9 +107,14 @@ class FusedAdam(torch.optim.Optimizer):
             hp.lr, (hp.beta1, hp.beta2), hp.eps, hp.weight_decay = group["lr"], group["betas"], group["eps"], \
                 group["weight_decay"]
             hp.ema_decay = self.ema_decay if self.ema_decay is not None else 0.0
-            hp.grad_scale, hp.step, hp.step_dev = 1.0, 1, L.ptr(self._step_dev)
+            hp.grad_scale, hp.step, hp.step_dev = float(getattr(self, "grad_scale", 1.0)), 1, L.ptr(self._step_dev)
             lr_dev = group.get("lr_dev")
             hp.lr_dev = L.ptr(lr_dev) if lr_dev is not None else None
             L.call("pddm_adam_ema_multi", table.data_ptr(), table.data_ptr() + C.sizeof(descs), len(blocks),
                    C.byref(hp), L.stream())
+        # the kernel wrote parameters (and EMA shadows) through raw pointers: ``_version`` did not move, so every
+        # cache of bf16 weight packs has to be told
+        from . import ops, plan
+        ops.invalidate_weight_cache()
+        plan.bump_weight_epoch()
         return loss

@@ -310,6 +310,24 @@ class UNetModel(nn.Module):
             raise RuntimeError("pddm_b200.UNetModel runs only on a CUDA sm_100a device (no CPU fallback)")
         out_dtype = x.dtype
         x = x.float().contiguous()
+        # Fast path: the hand-scheduled forward/backward plan (plan.py) for the configurations the reference ships.
+        if y is None and not (self.training and self.dropout > 0):
+            from . import plan as _plan
+            pl = _plan.plan_for(self, x)
+            if pl is not None:
+                if torch.is_grad_enabled() and any(p.requires_grad for p in pl.params):
+                    out = _plan.PlanFunction.apply(pl, x, timesteps, *pl.params)
+                else:
+                    pl.refresh_packs()
+                    out = pl.forward(x, timesteps, save=False)
+                return out if out_dtype == torch.float32 else out.to(out_dtype)
+        return self.forward_ops(x, timesteps, y).to(out_dtype)
+
+    def forward_ops(self, x, timesteps, y=None):
+        """The same network op by op through ``torch.ops.pddm.*`` (autograd derives the backward pass): every
+        configuration, incl. scale-shift norm, dropout, class conditioning, activation checkpointing."""
+        out_dtype = torch.float32
+        x = x.float().contiguous()
         _, emb = self.embed(timesteps.contiguous(), y)
         emb = self._emb_ctx(emb)
 
