@@ -258,12 +258,21 @@ def main():
     # gradient averaging: one flat all-reduce between backward and Adam.  --bucketed-allreduce issues it bucket by
     # bucket from inside backward on a communication stream; measured equal at 2 GPUs (the persistent GEMM kernels
     # leave NCCL no SM to overlap on), so the simpler form is the default.
-    hook = None
+    hook, optimizer = None, None
     if world > 1:
-        hook = parallel.BucketedGradAllReduce(eng.model.parameters()) if args.bucketed_allreduce else \
-            parallel.FlatGradAllReduce()
+        from probabilisticdeepdiffusionmodels_b200 import plan as _plan
+        from probabilisticdeepdiffusionmodels_b200.optim import FusedAdam
+        if args.bucketed_allreduce:
+            hook = parallel.BucketedGradAllReduce(eng.model.parameters())
+        elif _plan.plan_for(eng.model, x_dev) is not None:
+            # gradients live in one flat arena: all-reduce it in place, fold 1/W into the Adam kernel
+            optimizer = FusedAdam(eng.model.parameters(), lr=1e-4)
+            hook = parallel.ArenaGradAllReduce(optimizer)
+        else:
+            hook = parallel.FlatGradAllReduce()
 
-    step = eng.capture_train_step((B, 3, RES, RES), grad_hook=hook, overlap_wgrad=not args.no_overlap)
+    step = eng.capture_train_step((B, 3, RES, RES), optimizer=optimizer, grad_hook=hook,
+                                  overlap_wgrad=not args.no_overlap)
     kernels_per_step = step.state["kernels_per_step"]  # this library's kernels inside one captured step
 
     def barrier():

@@ -351,6 +351,8 @@ typedef struct {
   int32_t ld_dst;   /* elements between consecutive destination rows; 0 = dense (ntaps * Cin_pad | ntaps * Cout_pad):
                        lets several parameters be packed side by side into one wide GEMM operand */
   int32_t reserved;
+  void* dst2;       /* optional: the pack of the OTHER mode (same paddings, dense rows), written from the same tile
+                       of the fp32 source -- a conv needs both the forward and the data-gradient operand */
 } pddm_pack_desc;
 int pddm_pack_weights_multi(const void* descs, const void* blocks, int32_t nblocks, int32_t max_ntaps,
                             pddm_stream_t stream);

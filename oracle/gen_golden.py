@@ -293,7 +293,68 @@ def gen_hybrid():
     np.savez_compressed(os.path.join(GOLD, "hybrid.npz"), **out)
 
 
+TRAJ_STEPS = (900, 750, 500, 250, 100, 50, 20, 10, 5, 1)
+
+
+def gen_traj1000(which=("small", "cifar")):
+    """Full 1000-step reverse chains of the UNMODIFIED reference (src/engine.py:399-403, 510-554) with fixed x_T and a
+    seeded CPU generator for the per-step z (the test re-draws the same z sequence from the same seed), plus the
+    reference's OWN drift when its network runs under bf16 autocast -- the noise floor a bf16 implementation of the
+    same chain can be held to.  ``python -m oracle.gen_golden traj`` (the CIFAR chains take minutes on CPU)."""
+    from src.engine import Engine
+
+    out = {"steps": np.array(TRAJ_STEPS)}
+    path = os.path.join(GOLD, "traj1000.npz")
+    if os.path.exists(path):
+        out.update({k: v for k, v in np.load(path).items()})
+    cases = []
+    if "small" in which:
+        cases += [("small_linear", "unet_small_grey", 28, 2, "linear", 21), ("small_cosine", "unet_small_grey", 28, 2, "cosine", 21)]
+    if "cifar" in which:
+        cases += [("cifar_cosine", "unet", 32, 1, "cosine", 11)]
+    for tag, name, res, B, mode, pseed in cases:
+        cfg = MODEL_CONFIGS[name]
+        eng = Engine(dict(cfg), {"lr": 1e-3}, diffusion_steps=1000, mode=mode, resolution=res,
+                     clip_while_generating=True, sigma_mode="beta")
+        arch = arch_from_config(res, **{k: v for k, v in cfg.items() if k != "name"})
+        eng.model.load_state_dict(make_params(arch, seed=pseed))
+        eng.eval()
+        C = cfg["in_channels"]
+        xT = torch.from_numpy(np.random.RandomState(41).standard_normal((B, C, res, res)).astype(np.float32))
+        out[f"{tag}_xT"] = xT.numpy()
+        out[f"{tag}_zseed"] = np.array(4321)
+        gen = torch.Generator().manual_seed(4321)
+        chain = eng.sample_and_return_steps(xT.clone(), t_start=1000, steps_to_return=TRAJ_STEPS, generator=gen)
+        out[f"{tag}_chain"] = chain.numpy()
+        print(tag, "fp32 chain done", float(chain[:, -1].abs().max()), flush=True)
+        # the reference network under bf16 autocast, everything else (schedule tables, posterior math, z) unchanged
+        net = eng.model
+
+        class Autocast(torch.nn.Module):
+            in_channels = C
+
+            def forward(self, x, t):
+                with torch.autocast("cpu", dtype=torch.bfloat16):
+                    return net(x, t).float()
+
+        eng.model = Autocast()
+        gen = torch.Generator().manual_seed(4321)
+        chain16 = eng.sample_and_return_steps(xT.clone(), t_start=1000, steps_to_return=TRAJ_STEPS, generator=gen)
+        eng.model = net
+        d = (chain16 - chain).abs()
+        out[f"{tag}_floor_max"] = d.amax(dim=(0, 2, 3, 4)).numpy()
+        out[f"{tag}_floor_mean"] = d.mean(dim=(0, 2, 3, 4)).numpy()
+        print(tag, "bf16-autocast drift of the reference: max", out[f"{tag}_floor_max"], "mean", out[f"{tag}_floor_mean"],
+              flush=True)
+        np.savez_compressed(path, **out)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "traj":
+        ref_shims.install()
+        torch.set_num_threads(8)
+        gen_traj1000(tuple(sys.argv[2:]) or ("small", "cifar"))
+        return
     ref_shims.install()
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)

@@ -87,7 +87,7 @@ class WgradParams(C.Structure):
 
 class PackDesc(C.Structure):
     _fields_ = [("src", c_vp), ("dst", c_vp), ("Cout", c_i32), ("Cin", c_i32), ("ntaps", c_i32), ("mode", c_i32),
-                ("Cout_pad", c_i32), ("Cin_pad", c_i32), ("ld_dst", c_i32), ("reserved", c_i32)]
+                ("Cout_pad", c_i32), ("Cin_pad", c_i32), ("ld_dst", c_i32), ("reserved", c_i32), ("dst2", c_vp)]
 
 
 PACK_TILE = 32  # PDDM_PACK_TILE

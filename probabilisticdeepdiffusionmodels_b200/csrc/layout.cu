@@ -276,6 +276,7 @@ struct PackDesc {
   bf16* dst;
   int Cout, Cin, ntaps, mode, Cout_p, Cin_p;
   int ld_dst, reserved;  // ld_dst: elements between destination rows (0 = dense)
+  bf16* dst2;            // optional pack of the other mode (same paddings, dense) from the same source tile
 };
 constexpr int kPackTile = 32;
 __global__ void __launch_bounds__(256) pack_multi_kernel(const PackDesc* __restrict__ descs,
@@ -298,26 +299,32 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const PackDesc* __restr
   __syncthreads();
   // work item = one 16-byte store: (row of the destination tile, tap, piece of 8 channels)
   const int items = kPackTile * nt * (kPackTile / 8);
-  for (int it = threadIdx.x; it < items; it += blockDim.x) {
-    const int piece = it & 3, tap = (it >> 2) % nt, r = (it >> 2) / nt;
-    float v[8];
-    long long dst_off;
-    if (d.mode == 0) {  // dst[co][tap][ci]: r = output channel, piece = 8 input channels
-      const int co = co0 + r, ci = ci0 + piece * 8;
-      if (co >= d.Cout_p || ci >= d.Cin_p) continue;
+  for (int pass = 0; pass < 2; ++pass) {
+    bf16* dst = pass == 0 ? d.dst : d.dst2;
+    if (!dst) break;
+    const int mode = pass == 0 ? d.mode : 1 - d.mode;
+    const int ld = pass == 0 ? d.ld_dst : 0;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+      const int piece = it & 3, tap = (it >> 2) % nt, r = (it >> 2) / nt;
+      float v[8];
+      long long dst_off;
+      if (mode == 0) {  // dst[co][tap][ci]: r = output channel, piece = 8 input channels
+        const int co = co0 + r, ci = ci0 + piece * 8;
+        if (co >= d.Cout_p || ci >= d.Cin_p) continue;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = tile[r * pitch + (piece * 8 + j) * nt + tap];
-      dst_off = d.ld_dst ? static_cast<long long>(co) * d.ld_dst + tap * d.Cin_p + ci
-                         : (static_cast<long long>(co) * nt + tap) * d.Cin_p + ci;
-    } else {  // dst[ci][ntaps-1-tap][co]: r = input channel, piece = 8 output channels
-      const int ci = ci0 + r, co = co0 + piece * 8;
-      if (ci >= d.Cin_p || co >= d.Cout_p) continue;
+        for (int j = 0; j < 8; ++j) v[j] = tile[r * pitch + (piece * 8 + j) * nt + tap];
+        dst_off = ld ? static_cast<long long>(co) * ld + tap * d.Cin_p + ci
+                     : (static_cast<long long>(co) * nt + tap) * d.Cin_p + ci;
+      } else {  // dst[ci][ntaps-1-tap][co]: r = input channel, piece = 8 output channels
+        const int ci = ci0 + r, co = co0 + piece * 8;
+        if (ci >= d.Cin_p || co >= d.Cout_p) continue;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = tile[(piece * 8 + j) * pitch + r * nt + tap];
-      dst_off = d.ld_dst ? static_cast<long long>(ci) * d.ld_dst + (nt - 1 - tap) * d.Cout_p + co
-                         : (static_cast<long long>(ci) * nt + (nt - 1 - tap)) * d.Cout_p + co;
+        for (int j = 0; j < 8; ++j) v[j] = tile[(piece * 8 + j) * pitch + r * nt + tap];
+        dst_off = ld ? static_cast<long long>(ci) * ld + (nt - 1 - tap) * d.Cout_p + co
+                     : (static_cast<long long>(ci) * nt + (nt - 1 - tap)) * d.Cout_p + co;
+      }
+      *reinterpret_cast<uint4*>(dst + dst_off) = pack8(v);
     }
-    *reinterpret_cast<uint4*>(d.dst + dst_off) = pack8(v);
   }
 }
 // out[c] = sum_m x[m, c] for a small fp32 matrix (fixed order); block = 32 columns x 8 row lanes

@@ -66,6 +66,34 @@ class FlatGradAllReduce:
         torch._foreach_copy_(grads, views)
 
 
+class ArenaGradAllReduce:
+    """``hook(plan)`` for the hand-scheduled step (plan.py): the gradients are born in ONE flat fp32 arena, so the
+    all-reduce runs on it in place -- no gather / scatter copies, no scaling pass (the 1/W is folded into the fused
+    Adam kernel through ``optimizer.grad_scale``).  ``buckets`` > 1 splits the message into that many contiguous
+    all-reduces (NCCL pipelines them; useful when something else can run in between)."""
+
+    takes_plan = True
+
+    def __init__(self, optimizer=None, group=None, buckets=1):
+        self.group, self.buckets = group, buckets
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if optimizer is not None:
+            optimizer.grad_scale = 1.0 / world
+        self.scale_in_optimizer = optimizer is not None
+
+    def __call__(self, plan):
+        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return
+        flat = plan.grad_arena
+        n = flat.numel()
+        step = -(-n // self.buckets)
+        step = (step + 1023) // 1024 * 1024
+        for lo in range(0, n, step):
+            dist.all_reduce(flat[lo: lo + step], op=dist.ReduceOp.SUM, group=self.group)
+        if not self.scale_in_optimizer:
+            flat.mul_(1.0 / dist.get_world_size(self.group))
+
+
 class BucketedGradAllReduce:
     """Gradient averaging that overlaps the backward pass: ``hook = BucketedGradAllReduce(params)`` registers a
     post-accumulate-grad hook on every parameter; as soon as the gradients of one bucket (parameters in the order

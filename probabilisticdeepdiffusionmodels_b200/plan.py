@@ -236,16 +236,19 @@ class UNetPlan:
         # ---------------- pack arena (bf16 GEMM operands) + descriptor table of the one-launch re-pack
         descs, total = [], 0
 
-        def add(g, mode):
+        def add(g, mode, both=False):
             nonlocal total
             n = g.cop * g.cip * g.ntaps
-            descs.append((g, mode, total))
-            total += (n + 7) // 8 * 8
+            n8 = (n + 7) // 8 * 8
+            descs.append((g, mode, total, total + n8 if both else None))
+            total += n8 * (2 if both else 1)
 
         for g in self.gemms:
-            if g.need_fwd:
+            if g.need_fwd and g.need_dgrad:
+                add(g, 0, both=True)  # one source tile feeds the forward and the data-gradient operand
+            elif g.need_fwd:
                 add(g, 0)
-            if g.need_dgrad:
+            elif g.need_dgrad:
                 add(g, 1)
         emb0, emb1 = total, total + self.sumC * self.E
         total += 2 * self.sumC * self.E
@@ -253,25 +256,27 @@ class UNetPlan:
         tab = (L.PackDesc * (len(descs) + 2 * len(emb_w)))()
         blocks = []
 
-        def fill(i, src, dst_ptr, cout, cin, nt, mode, cop, cip, ld_dst=0):
+        def fill(i, src, dst_ptr, cout, cin, nt, mode, cop, cip, ld_dst=0, dst2=None):
             d = tab[i]
-            d.src, d.dst = src.data_ptr(), dst_ptr
+            d.src, d.dst, d.dst2 = src.data_ptr(), dst_ptr, dst2
             d.Cout, d.Cin, d.ntaps, d.mode, d.Cout_pad, d.Cin_pad, d.ld_dst = cout, cin, nt, mode, cop, cip, ld_dst
             tiles = -(-cop // L.PACK_TILE) * -(-cip // L.PACK_TILE)
             blocks.extend((i, t_) for t_ in range(tiles))
 
         i = 0
         base = self.pack_arena.data_ptr()
-        for g, mode, o in descs:
+        for g, mode, o, o2 in descs:
             n = g.cop * g.cip * g.ntaps
             view = self.pack_arena[o: o + n].view((g.cop, g.ntaps, g.cip) if mode == 0 else (g.cip, g.ntaps, g.cop))
             if mode == 0:
                 g.pack0 = view
             else:
                 g.pack1 = view
+            if o2 is not None:
+                g.pack1 = self.pack_arena[o2: o2 + n].view(g.cip, g.ntaps, g.cop)
             src = g.pack_view if g.pack_view is not None else g.w
             cout, cin, nt = (src.shape[0], src.shape[1], src.numel() // (src.shape[0] * src.shape[1]))
-            fill(i, src, base + 2 * o, cout, cin, nt, mode, g.cop, g.cip)
+            fill(i, src, base + 2 * o, cout, cin, nt, mode, g.cop, g.cip, dst2=None if o2 is None else base + 2 * o2)
             i += 1
         # emb_layers: 30 [Cout_i, E] matrices side by side = one [sumC, E] operand (forward) and its transpose
         self.emb_all.pack0 = self.pack_arena[emb0: emb0 + self.sumC * self.E].view(self.sumC, 1, self.E)

@@ -112,3 +112,37 @@ def test_single_process_is_a_noop():
     p.grad = torch.full((3,), 2.0)
     FlatGradAllReduce()([p])
     assert p.grad.tolist() == [2.0, 2.0, 2.0]
+
+
+def _worker_arena(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from probabilisticdeepdiffusionmodels_b200 import parallel
+    parallel.init_from_env("gloo")
+
+    class Plan:  # what ArenaGradAllReduce needs of plan.UNetPlan: the flat fp32 gradient arena
+        grad_arena = torch.arange(5000, dtype=torch.float32) * (rank + 1)
+
+    class Opt:
+        grad_scale = 1.0
+
+    opt = Opt()
+    for buckets in (1, 3):
+        Plan.grad_arena = torch.arange(5000, dtype=torch.float32) * (rank + 1)
+        parallel.ArenaGradAllReduce(opt, buckets=buckets)(Plan)
+        assert opt.grad_scale == 1.0 / world  # the 1/W lives in the optimizer kernel
+        want = torch.arange(5000, dtype=torch.float32) * sum(r + 1 for r in range(world))
+        assert torch.equal(Plan.grad_arena, want)
+    Plan.grad_arena = torch.ones(100) * (rank + 1)
+    parallel.ArenaGradAllReduce(None)(Plan)  # no optimizer to carry the scale: averaged in place
+    assert torch.allclose(Plan.grad_arena, torch.full((100,), 1.5))
+    if rank == 0:
+        torch.save({"ok": True}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_arena_grad_allreduce(tmp_path):
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_worker_arena, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert torch.load(out)["ok"]
