@@ -388,6 +388,9 @@ int pddm_nhwc_slice_to_nchw(const float* src, float* dst, int32_t B, int32_t C, 
  * QKVAttention (src/modules/unet.py:237-256): per (sample, head), softmax_fp32((q*s)(k*s)^T) v, s = d^-1/4.
  * qkv: bf16 [B, T, 3*heads*d] with the reference's head-major [q|k|v] channel packing; out: bf16 [B, T, heads*d].
  * lse [B, heads, T] fp32 is saved for the backward.  d in {32, 64, 96, 128}, T <= 256.
+ * The backward of a head with more than 128 keys runs as two cooperating CTAs (one per 128-key tile) that exchange
+ * their fp32 partial dQ products through the caller-owned workspace `ws` (pddm_attn_bwd_workspace_bytes, 0 when
+ * T <= 128; contents are scratch).
  * ---------------------------------------------------------------------------------------------------- */
 typedef struct {
   const void* qkv;
@@ -403,7 +406,10 @@ typedef struct {
   const float* lse;
   void* dqkv; /* bf16 [B, T, 3*heads*d] */
   int32_t B, T, heads, d;
+  void* ws;   /* >= pddm_attn_bwd_workspace_bytes(B, T, heads, d) bytes, 16-byte aligned; may be NULL when T <= 128 */
+  int64_t ws_bytes;
 } pddm_attn_bwd_params;
+int64_t pddm_attn_bwd_workspace_bytes(int32_t B, int32_t T, int32_t heads, int32_t d);
 int pddm_attn_bwd(const pddm_attn_bwd_params* p, pddm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------

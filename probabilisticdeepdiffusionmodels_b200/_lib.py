@@ -99,7 +99,7 @@ class AttnFwdParams(C.Structure):
 
 class AttnBwdParams(C.Structure):
     _fields_ = [("qkv", c_vp), ("out", c_vp), ("dout", c_vp), ("lse", c_vp), ("dqkv", c_vp), ("B", c_i32),
-                ("T", c_i32), ("heads", c_i32), ("d", c_i32)]
+                ("T", c_i32), ("heads", c_i32), ("d", c_i32), ("ws", c_vp), ("ws_bytes", c_i64)]
 
 
 class AdamParams(C.Structure):
@@ -154,6 +154,7 @@ SIGNATURES = {
     "pddm_nhwc_slice_to_nchw": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "pddm_attn_fwd": (c_i32, [P(AttnFwdParams), c_vp]),
     "pddm_attn_bwd": (c_i32, [P(AttnBwdParams), c_vp]),
+    "pddm_attn_bwd_workspace_bytes": (c_i64, [c_i32, c_i32, c_i32, c_i32]),
     "pddm_adam_ema_step": (c_i32, [P(AdamParams), c_vp]),
     "pddm_adam_ema_multi": (c_i32, [c_vp, c_vp, c_i32, P(AdamParams), c_vp]),
     "pddm_counter_add": (c_i32, [c_vp, c_i32, c_vp]),

@@ -458,6 +458,9 @@ def attn_bwd(qkv, out, dout, lse, heads):
     p = L.AttnBwdParams()
     p.qkv, p.out, p.dout, p.lse, p.dqkv = L.ptr(qkv), L.ptr(out), L.ptr(dout), L.ptr(lse), L.ptr(dqkv)
     p.B, p.T, p.heads, p.d = B, T, heads, C3 // 3 // heads
+    nws = L.load().pddm_attn_bwd_workspace_bytes(B, T, heads, p.d)  # two key tiles exchange fp32 partial dQ products
+    ws = _ws(nws, qkv.device) if nws else None
+    p.ws, p.ws_bytes = (L.ptr(ws) if nws else None), nws
     L.call("pddm_attn_bwd", C.byref(p), L.stream())
     return dqkv
 

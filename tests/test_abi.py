@@ -44,6 +44,7 @@ def test_struct_sizes_match_header_layout():
     assert ctypes.sizeof(L.Tables) == 12 * p + 8
     assert ctypes.sizeof(L.PackDesc) == 3 * p + 8 * i
     assert ctypes.sizeof(L.AttnFwdParams) == 3 * p + 4 * i
+    assert ctypes.sizeof(L.AttnBwdParams) == 5 * p + 4 * i + p + 8
     assert ctypes.sizeof(L.ConvParams) == 6 * p + 3 * i + 8 * i + 4 * 9 * i + i + 6 * i + p + 2 * i
     assert ctypes.sizeof(L.AdamParams) % 8 == 0 and ctypes.sizeof(L.GnBwdParams) % 8 == 0
 
