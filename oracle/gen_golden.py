@@ -349,7 +349,57 @@ def gen_traj1000(which=("small", "cifar")):
         np.savez_compressed(path, **out)
 
 
+def gen_floors():
+    """The reference's OWN error when its network runs under bf16 autocast instead of fp32 (same inputs as the unet /
+    unet_big / engine fixtures): relative L2 of eps and relative deviation of the loss.  This is the noise floor of a
+    bf16-operand implementation of the same network; the GPU tests print it next to the measured error of the CUDA
+    path.  ``python -m oracle.gen_golden floors`` -> tests/golden/floors.npz."""
+    from src.engine import Engine
+
+    out = {}
+
+    def rel(a, b):
+        return float((a.double() - b.double()).norm() / b.double().norm())
+
+    cases = [("tiny", TINY, 16, 2, 1), ("tiny_ss", dict(TINY, use_scale_shift_norm=True), 16, 2, 1),
+             ("tiny_sigma", TINY, 16, 2, 2), ("small_grey28", MODEL_CONFIGS["unet_small_grey"], 28, 2, 1),
+             ("small_grey32", MODEL_CONFIGS["unet_small_grey"], 32, 2, 1), ("cifar", MODEL_CONFIGS["unet"], 32, 1, 1),
+             ("cifar_sigma", MODEL_CONFIGS["unet"], 32, 1, 2), ("celeba64", MODEL_CONFIGS["unet_celeba"], 64, 1, 1)]
+    for tag, cfg, res, b, out_mult in cases:
+        m, arch, P = ref_model(cfg, res, seed=11, out_mult=out_mult)
+        x0, t, noise = synth_batch(3, b, cfg["in_channels"], res, 1000)
+        with torch.no_grad():
+            y = m(noise, t)
+            with torch.autocast("cpu", dtype=torch.bfloat16):
+                y16 = m(noise, t).float()
+        out[f"{tag}_eps_rel"] = np.array(rel(y16, y))
+        print(tag, "reference bf16-autocast eps rel-L2", out[f"{tag}_eps_rel"], flush=True)
+    for mode in ("linear", "cosine"):
+        cfg = MODEL_CONFIGS["unet_small_grey"]
+        eng = Engine(dict(cfg), {"lr": 1e-3}, diffusion_steps=1000, mode=mode, resolution=28,
+                     clip_while_generating=True, sigma_mode="beta")
+        arch = arch_from_config(28, **{k: v for k, v in cfg.items() if k != "name"})
+        eng.model.load_state_dict(make_params(arch, seed=21))
+        x0, t, noise = synth_batch(9, 4, 1, 28, 1000)
+        t[0], t[1] = 1, 1000
+        with torch.no_grad():
+            x_t = eng.get_q_t(x0, noise, t)
+            eps = eng.model(x_t, t)
+            with torch.autocast("cpu", dtype=torch.bfloat16):
+                eps16 = eng.model(x_t, t).float()
+            loss = eng.get_loss(eps, noise, x0, x_t, t=t, update_loss_log=False)
+            loss16 = eng.get_loss(eps16, noise, x0, x_t, t=t, update_loss_log=False)
+        out[f"engine_{mode}_eps_rel"] = np.array(rel(eps16, eps))
+        out[f"engine_{mode}_loss_rel"] = np.array(abs(loss16.item() - loss.item()) / abs(loss.item()))
+        print(mode, "engine eps", out[f"engine_{mode}_eps_rel"], "loss", out[f"engine_{mode}_loss_rel"], flush=True)
+    np.savez_compressed(os.path.join(GOLD, "floors.npz"), **out)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "floors":
+        ref_shims.install()
+        gen_floors()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "traj":
         ref_shims.install()
         torch.set_num_threads(8)

@@ -5,6 +5,7 @@ import pytest
 import torch
 
 from oracle.unet_ref import MODEL_CONFIGS, arch_from_config, make_params
+from _parity import within
 
 pytestmark = pytest.mark.gpu
 CFG = MODEL_CONFIGS["unet_small_grey"]
@@ -32,16 +33,20 @@ def test_train_step_matches_reference(golden, mode):
     np.testing.assert_array_equal(x_t.cpu().numpy(), g[f"{mode}_x_t"])  # q_sample is bit exact
     eps = eng.model(x_t, t)
     rel = float((eps.cpu() - T(g[f"{mode}_eps"])).norm() / T(g[f"{mode}_eps"]).norm())
-    assert rel < 1.5e-2, rel  # bf16 network vs fp32 reference, relative L2
+    # bf16 network vs fp32 reference, relative L2 (bounds: 1.5 x measured on B200)
+    within(f"engine[{mode}] eps rel-L2", rel, 1.55e-2, f"engine_{mode}_eps_rel")
     loss = eng.get_loss(eps, noise, x0, x_t, t=t, update_loss_log=False)
-    # north_star: loss within 1e-3 relative would need fp32 activations; bf16 activations give ~3e-3 here
-    assert abs(loss.item() - float(g[f"{mode}_loss"])) / float(g[f"{mode}_loss"]) < 1e-2
+    # north_star: loss within 1e-3 relative -- met (1.1e-4 / 1.8e-4 measured)
+    within(f"engine[{mode}] loss relative deviation", abs(loss.item() - float(g[f"{mode}_loss"])) / float(g[f"{mode}_loss"]),
+           3e-4, f"engine_{mode}_loss_rel")
     wl = eng.get_loss(eps, noise, x0, x_t, t=t, weights=T(g[f"{mode}_w"]).cuda(), update_loss_log=False)
     assert wl.dtype == torch.float64  # importance weights are float64 (src/sampling/importance_sampler.py:33,37)
-    assert abs(wl.item() - float(g[f"{mode}_wloss"])) / float(g[f"{mode}_wloss"]) < 1e-2
+    within(f"engine[{mode}] weighted loss relative deviation",
+           abs(wl.item() - float(g[f"{mode}_wloss"])) / float(g[f"{mode}_wloss"]), 4e-4)
     loss.backward()
     gn = float(eng.compute_grad_norm(eng.model.parameters()))
-    assert abs(gn - float(g[f"{mode}_gradnorm"])) / float(g[f"{mode}_gradnorm"]) < 3e-2
+    within(f"engine[{mode}] gradient-norm relative deviation",
+           abs(gn - float(g[f"{mode}_gradnorm"])) / float(g[f"{mode}_gradnorm"]), 1e-4)
     # one Adam step: first-step update is lr*sign(g); compare where the reference moved
     opt = torch.optim.Adam(eng.parameters(), lr=1e-3)
     opt.step()
@@ -65,9 +70,10 @@ def test_50_step_chain_matches_reference(golden, mode, sigma_mode, clip):
     out = eng.sample_and_return_steps(T(g["chain_xT"]).cuda(), t_start=50, steps_to_return=(25, 10, 1), fixed_noise=zs)
     ref = g[f"{mode}_{sigma_mode}_clip{int(clip)}_chain"]
     assert tuple(out.shape) == ref.shape
-    # per-pixel tolerance for a 50-step trajectory with a bf16 network: 5e-2 absolute on values of O(1)
+    # per-pixel tolerance for a 50-step trajectory with a bf16 network (1.5 x measured), values of O(1)
     err = np.abs(out.numpy() - ref)
-    assert err.max() < 5e-2 and err.mean() < 5e-3, (err.max(), err.mean())
+    within(f"50-step chain[{mode},{sigma_mode},clip={clip}] max |delta| per pixel", float(err.max()), 5.5e-3)
+    within(f"50-step chain[{mode},{sigma_mode},clip={clip}] mean |delta| per pixel", float(err.mean()), 8e-4)
 
 
 def test_graph_chain_equals_eager_chain():
