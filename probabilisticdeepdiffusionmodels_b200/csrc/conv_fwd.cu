@@ -508,10 +508,33 @@ conv_fwd_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int tw = tile % a.tiles_w, th = (tile / a.tiles_w) % a.tiles_h, tb = tile / (a.tiles_w * a.tiles_h);
+      const int c_lo = eg * (8 / (kSwapEpiWarps / 4)), c_hi = c_lo + 8 / (kSwapEpiWarps / 4);
+      // pixel-major role of this lane: pixel i*8 + lane/4 of a 32-pixel chunk, 8 channels from n
+      const int piece = lane & 3;
+      const int n = q * 32 + piece * 8;
+      // element offset of that pixel (chunk c, group i) in the NHWC output / residual, or -1 outside the tensor
+      auto pix_off = [&](int c, int i) -> long long {
+        const int p = c * 32 + i * 8 + (lane >> 2);
+        const int bb = p / rpb, rr = p - bb * rpb;
+        const int hh = rr >> wshift, ww = rr & wmask;
+        const int b = tb * a.BB + bb, h = th * a.BH + hh, w = tw * a.BW + ww;
+        const bool valid = (bb < a.BB) && (b < a.B) && (h < a.H) && (w < a.W) && (n < a.Cout);
+        return valid ? ((static_cast<long long>(b) * a.H + h) * a.W + w) * a.Cout + n : -1ll;
+      };
+      // The residual of chunk c+1 is fetched while chunk c is transposed and stored, and the first chunk's while the
+      // main loop of this tile is still running: the 16-byte loads never sit on the drain's critical path.
+      uint4 rres[2][4];
+      if (res) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const long long off = pix_off(c_lo, i);
+          if (off >= 0) rres[0][i] = __ldg(reinterpret_cast<const uint4*>(
+                            reinterpret_cast<const __nv_bfloat16*>(a.residual) + off));
+        }
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
-      const int c_lo = eg * (8 / (kSwapEpiWarps / 4)), c_hi = c_lo + 8 / (kSwapEpiWarps / 4);
       uint32_t r[2][32];
       tmem_ld32(taddr + c_lo * 32, r[0]);
 #pragma unroll 1
@@ -520,7 +543,17 @@ conv_fwd_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int ci = 0; ci < 2; ++ci) {
           const int c = cp + ci;
           tmem_ld_wait();
-          if (c + 1 < c_hi) tmem_ld32(taddr + (c + 1) * 32, r[ci ^ 1]);
+          if (c + 1 < c_hi) {
+            tmem_ld32(taddr + (c + 1) * 32, r[ci ^ 1]);
+            if (res) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const long long off = pix_off(c + 1, i);
+                if (off >= 0) rres[ci ^ 1][i] = __ldg(reinterpret_cast<const uint4*>(
+                                  reinterpret_cast<const __nv_bfloat16*>(a.residual) + off));
+              }
+            }
+          }
           // ---- channel-major part: + bias + per-sample broadcast, park the 32 pixels of this channel
           const int bs = tb * a.BB + (c * 32) / rpb;  // the 32 pixels of a chunk belong to one sample
           float add = bias_v;
@@ -530,25 +563,17 @@ conv_fwd_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           for (int j = 0; j < 32; ++j)
             *reinterpret_cast<float*>(stg + j * kSwapPitch + lane * 4) = __uint_as_float(r[ci][j]) + add;
           __syncwarp();
-          // ---- pixel-major part: lane -> (pixel i*8 + lane/4, 8 channels lane%4), residual, pack, store
-          const int piece = lane & 3;
-          const int n = q * 32 + piece * 8;
+          // ---- pixel-major part: residual, pack, store
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int pl = i * 8 + (lane >> 2);
-            const int p = c * 32 + pl;
-            const int bb = p / rpb, rr = p - bb * rpb;
-            const int hh = rr >> wshift, ww = rr & wmask;
-            const int b = tb * a.BB + bb, h = th * a.BH + hh, w = tw * a.BW + ww;
-            const bool valid = (bb < a.BB) && (b < a.B) && (h < a.H) && (w < a.W) && (n < a.Cout);
+            const long long off = pix_off(c, i);
             const float4 v0 = *reinterpret_cast<const float4*>(stg + pl * kSwapPitch + piece * 32);
             const float4 v1 = *reinterpret_cast<const float4*>(stg + pl * kSwapPitch + piece * 32 + 16);
-            if (valid) {
+            if (off >= 0) {
               float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-              const size_t off = ((static_cast<size_t>(b) * a.H + h) * a.W + w) * a.Cout + n;
               if (res) {
-                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(
-                    reinterpret_cast<const __nv_bfloat16*>(a.residual) + off));
+                const uint4 rv = rres[ci][i];
                 const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
