@@ -38,6 +38,8 @@ struct ConvKArgs {
   int nacc;  // accumulator stages in TMEM (2 = epilogue overlaps the next tile's main loop)
   int dbg;   // PDDM_CONV_DBG experiment bits: 1 = empty epilogue, 2 = no A loads, 4 = no MMAs, 8 = no B loads
   uint32_t idesc, layout_type, sbo_bytes, tmem_cols;
+  int epi_tma;             // 1: bulk-tensor epilogue (conv_fwd_kernel): output leaves and the residual arrives by TMA
+  uint32_t off_out, off_res;  // byte offsets of the 2 x 16 KB output / residual staging buffers
 };
 
 constexpr int kConvThreads = 256;
@@ -48,7 +50,8 @@ constexpr int kAddBytes = kMaxAddRows * 256 * 4;  // smem for the staged bias + 
 
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvKArgs a) {
+                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY,
+                const __grid_constant__ CUtensorMap tmR, const __grid_constant__ ConvKArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int mt = a.mt;
@@ -61,6 +64,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tmem_full = bars + 2 * kMaxStages;    // [2]
   uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;  // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  uint64_t* res_full = bars + 2 * kMaxStages + 6;  // [2] residual staging buffers (bulk-tensor epilogue)
   float* smem_add = reinterpret_cast<float*>(smem + nstages * stage_bytes + 512);
 
   const int warp = threadIdx.x >> 5;
@@ -81,6 +85,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], 4);
+      mbar_init(&res_full[s], 1);
     }
     fence_mbar_init();
   }
@@ -226,6 +231,126 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int nchunks = a.block_n >> 5;
     const bool has_add = (a.bias != nullptr) || (a.bcast != nullptr);
     const bool stage_add = has_add && a.BB <= kMaxAddRows;
+    if (a.epi_tma) {
+      // -------------------------------------------------------------- bulk-tensor epilogue
+      // The tile leaves in 64-channel slices: each thread converts its pixel row (TMEM lane) of a slice and writes the
+      // 128 bytes into a double-buffered staging tile laid out like a TMA operand (128 B rows, 128 B swizzle); one
+      // elected thread hands the slice to the TMA unit (one bulk tensor store, rows outside the tensor clipped) and
+      // the warps go on with the next slice.  The residual arrives the same way, two slices ahead -- the first two
+      // of a tile while its main loop is still running -- so the drain never waits on a global load, and per-thread
+      // 16-byte stores to 128 different rows (one sector each) are gone.  Requires 128-pixel tiles, bf16 output,
+      // identity output map, Cout % 64 == 0 (host-checked).
+      uint8_t* out_stage = smem + a.off_out;
+      uint8_t* res_stage = smem + a.off_res;
+      const bool res = a.residual != nullptr;
+      uint32_t sl = 0;  // running slice counter: staging buffer = sl & 1, residual barrier parity = (sl >> 1) & 1
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile / m_tiles;
+        const int m_tile = tile % m_tiles;
+        const int tw = m_tile % a.tiles_w;
+        const int th = (m_tile / a.tiles_w) % a.tiles_h;
+        const int tb = m_tile / (a.tiles_w * a.tiles_h);
+        const int w0 = tw * a.BW, h0 = th * a.BH, b0 = tb * a.BB;
+        const int nbase = n_tile * a.block_n;
+        int nsl = (a.Cout - nbase) >> 6;
+        if (nsl > (a.block_n >> 6)) nsl = a.block_n >> 6;
+        const int bb = row / rows_per_b;
+        if (stage_add) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers are done
+          const int total = a.BB * a.block_n;
+          for (int i = etid; i < total; i += 128) {
+            const int sb = i / a.block_n, n = nbase + (i - sb * a.block_n);
+            float v = 0.f;
+            if (n < a.Cout) {
+              if (a.bias) v = __ldg(a.bias + n);
+              const int gb = b0 + sb;
+              if (a.bcast && gb < a.B) v += __ldg(a.bcast + static_cast<size_t>(gb) * a.ld_bcast + n);
+            }
+            smem_add[i] = v;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        const float* addrow = smem_add + (bb < a.BB ? bb : 0) * a.block_n;
+        if (res && etid == 0) {
+          for (int s2 = 0; s2 < 2 && s2 < nsl; ++s2) {
+            const uint32_t buf = (sl + s2) & 1;
+            mbar_expect_tx(&res_full[buf], 128 * 128);
+            tma_load_4d(res_stage + buf * (128 * 128), &tmR, &res_full[buf], nbase + 64 * s2, w0, h0, b0);
+          }
+        }
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * a.block_n;
+        for (int s2 = 0; s2 < nsl; ++s2, ++sl) {
+          const uint32_t buf = sl & 1;
+          uint32_t r0[32], r1[32];
+          tmem_ld32(taddr + s2 * 64, r0);
+          tmem_ld32(taddr + s2 * 64 + 32, r1);
+          if (res) mbar_wait(&res_full[buf], (sl >> 1) & 1);
+          tmem_ld_wait();
+          uint8_t* orow = out_stage + buf * (128 * 128) + row * 128;
+          const uint8_t* rrow = res_stage + buf * (128 * 128) + row * 128;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {  // 16-byte units of the row: channels [8u, 8u + 8) of the slice
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(u < 4 ? r0[u * 8 + j] : r1[(u - 4) * 8 + j]);
+            if (has_add) {
+              if (stage_add) {
+                const float4 a0 = *reinterpret_cast<const float4*>(addrow + s2 * 64 + u * 8);
+                const float4 a1 = *reinterpret_cast<const float4*>(addrow + s2 * 64 + u * 8 + 4);
+                v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
+                v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+              } else {
+                const int n = nbase + s2 * 64 + u * 8;
+                const int gb = b0 + bb < a.B ? b0 + bb : a.B - 1;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  if (a.bias) v[j] += __ldg(a.bias + n + j);
+                  if (a.bcast) v[j] += __ldg(a.bcast + static_cast<size_t>(gb) * a.ld_bcast + n + j);
+                }
+              }
+            }
+            const int su = (u ^ (row & 7)) << 4;
+            if (res) {
+              const uint4 rv = *reinterpret_cast<const uint4*>(rrow + su);
+              const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
+                v[2 * j] += __low2float(h2);
+                v[2 * j + 1] += __high2float(h2);
+              }
+            }
+            *reinterpret_cast<uint4*>(orow + su) =
+                make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+          }
+          if (s2 + 1 == nsl) {  // every TMEM read of this warp has completed: hand the accumulator back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          }
+          fence_proxy_async();
+          // the staging buffer the NEXT slice will fill was handed to the TMA unit one slice ago: once that store has
+          // read it (it has had a whole slice of time), everybody may overwrite it after the barrier
+          if (etid == 0) bulk_wait_group_read<0>();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (etid == 0) {
+            tma_store_4d(&tmY, out_stage + buf * (128 * 128), nbase + 64 * s2, w0, h0, b0);
+            bulk_commit_group();
+            if (res && s2 + 2 < nsl) {  // this residual buffer has been read by everyone: refill it two slices ahead
+              mbar_expect_tx(&res_full[buf], 128 * 128);
+              tma_load_4d(res_stage + buf * (128 * 128), &tmR, &res_full[buf], nbase + 64 * (s2 + 2), w0, h0, b0);
+            }
+          }
+        }
+        if (++acc == nacc) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+      if (etid == 0) bulk_wait_group<0>();
+    } else
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
      const int n_tile = tile / m_tiles;
      for (int hf = 0; hf < mt; ++hf) {
@@ -769,13 +894,21 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
   while (cols < static_cast<uint32_t>(a.nacc * a.mt * a.block_n)) cols <<= 1;
   a.tmem_cols = cols;
   const int stage_bytes = a.mt * a.a_slot_bytes + a.b_bytes;
-  const int budget = device_info().max_smem_optin - 1024 - 512 - kAddBytes;
+  // bulk-tensor epilogue (see the kernel): 2 x 16 KB output staging (+ 2 x 16 KB residual staging)
+  a.epi_tma = (!(env_knobs().conv_dbg > 0 && (env_knobs().conv_dbg & 16)) && p->y_dtype == PDDM_BF16 &&
+               p->out_sh == 1 && p->out_sw == 1 && p->out_oh == 0 && p->out_ow == 0 && p->out_H == p->H &&
+               p->out_W == p->W && p->Cout % 64 == 0 && a.block_n % 64 == 0 && a.mt == 1 &&
+               a.BW * a.BH * a.BB == 128 && (!p->residual || p->res_dtype == PDDM_BF16)) ? 1 : 0;
+  const int epi_bytes = a.epi_tma ? (p->residual ? 4 : 2) * 128 * 128 + 1024 : 0;
+  const int budget = device_info().max_smem_optin - 1024 - 512 - kAddBytes - epi_bytes;
   int stages = budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (env_knobs().conv_stages > 0 && env_knobs().conv_stages < stages) stages = env_knobs().conv_stages;
   if (stages < 2) return PDDM_ERR_UNSUPPORTED;
   a.stages = stages;
-  const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 + 512 + kAddBytes;
+  a.off_out = (static_cast<uint32_t>(stages) * stage_bytes + 512 + kAddBytes + 1023) / 1024 * 1024;
+  a.off_res = a.off_out + 2 * 128 * 128;
+  const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 + 512 + kAddBytes + epi_bytes;
 
   CUtensorMap tmA, tmA2, tmB;
   const int cin_a = p->x2 ? p->Cin_a : p->Cin;
@@ -806,9 +939,21 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
     int rc = make_tmap_bf16(&tmB, p->w, 2, dims, str, box, swz);
     if (rc) return rc;
   }
+  CUtensorMap tmY = tmA, tmR = tmA;
+  if (a.epi_tma) {
+    const uint64_t dims[4] = {static_cast<uint64_t>(p->Cout), static_cast<uint64_t>(p->W), static_cast<uint64_t>(p->H),
+                              static_cast<uint64_t>(p->B)};
+    const uint64_t str[3] = {static_cast<uint64_t>(p->Cout) * 2, static_cast<uint64_t>(p->W) * p->Cout * 2,
+                             static_cast<uint64_t>(p->H) * p->W * p->Cout * 2};
+    const uint32_t box[4] = {64, static_cast<uint32_t>(a.BW), static_cast<uint32_t>(a.BH), static_cast<uint32_t>(a.BB)};
+    int rc = make_tmap_bf16(&tmY, p->y, 4, dims, str, box, 128);
+    if (rc) return rc;
+    tmR = tmY;
+    if (p->residual && (rc = make_tmap_bf16(&tmR, p->residual, 4, dims, str, box, 128))) return rc;
+  }
   if (ensure_smem_optin(reinterpret_cast<const void*>(conv_fwd_kernel))) return PDDM_ERR_CUDA;
   const int total_tiles = ((a.m_tiles + a.mt - 1) / a.mt) * a.n_tiles;
   const int grid = total_tiles < device_info().sm_count ? total_tiles : device_info().sm_count;
-  PdlLaunch(grid, kConvThreads, smem_bytes, stream)(conv_fwd_kernel, tmA, tmA2, tmB, a);
+  PdlLaunch(grid, kConvThreads, smem_bytes, stream)(conv_fwd_kernel, tmA, tmA2, tmB, tmY, tmR, a);
   return launch_status();
 }
