@@ -42,7 +42,7 @@ struct ConvKArgs {
   uint32_t off_out, off_res;  // byte offsets of the 2 x 16 KB output / residual staging buffers
 };
 
-constexpr int kConvThreads = 256;
+constexpr int kConvThreads = 384;  // warp 0 MMA, warps 1-3 TMA producers, warps 4-11 epilogue (two per TMEM lane quadrant)
 constexpr int kMaxStages = 8;
 constexpr int kNumProducers = 3;
 constexpr int kMaxAddRows = 8;                   // tile rows may span up to this many samples with a staged bias/bcast
@@ -64,7 +64,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tmem_full = bars + 2 * kMaxStages;    // [2]
   uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;  // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
-  uint64_t* res_full = bars + 2 * kMaxStages + 6;  // [2] residual staging buffers (bulk-tensor epilogue)
+  uint64_t* res_full = bars + 2 * kMaxStages + 6;  // [2 groups][2] residual staging buffers (bulk-tensor epilogue)
   float* smem_add = reinterpret_cast<float*>(smem + nstages * stage_bytes + 512);
 
   const int warp = threadIdx.x >> 5;
@@ -84,9 +84,9 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);
-      mbar_init(&res_full[s], 1);
+      mbar_init(&tmem_empty[s], a.epi_tma ? 8 : 4);
     }
+    for (int s = 0; s < 4; ++s) mbar_init(&res_full[s], 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_ptr, a.tmem_cols);
@@ -224,7 +224,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int etid = threadIdx.x - 128;  // 0..127
+    const int etid = threadIdx.x - 128;  // 0..255 (0..127 on the direct-store path, which uses warps 4-7 only)
     int acc = 0;
     uint32_t acc_phase = 0;
     const int rows_per_b = a.BW * a.BH;
@@ -232,18 +232,23 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const bool has_add = (a.bias != nullptr) || (a.bcast != nullptr);
     const bool stage_add = has_add && a.BB <= kMaxAddRows;
     if (a.epi_tma) {
-      // -------------------------------------------------------------- bulk-tensor epilogue
-      // The tile leaves in 64-channel slices: each thread converts its pixel row (TMEM lane) of a slice and writes the
-      // 128 bytes into a double-buffered staging tile laid out like a TMA operand (128 B rows, 128 B swizzle); one
-      // elected thread hands the slice to the TMA unit (one bulk tensor store, rows outside the tensor clipped) and
-      // the warps go on with the next slice.  The residual arrives the same way, two slices ahead -- the first two
-      // of a tile while its main loop is still running -- so the drain never waits on a global load, and per-thread
-      // 16-byte stores to 128 different rows (one sector each) are gone.  Requires 128-pixel tiles, bf16 output,
-      // identity output map, Cout % 64 == 0 (host-checked).
-      uint8_t* out_stage = smem + a.off_out;
-      uint8_t* res_stage = smem + a.off_res;
+      // -------------------------------------------------------------- bulk-tensor epilogue (8 warps)
+      // A single epilogue warp per scheduler drains a 128 x 256 accumulator in ~4 us (every dependent-instruction
+      // stall is exposed), far longer than the 1.2 us main loop of a 1x1 convolution -- so TWO warps share each TMEM
+      // lane quadrant and take alternate 32-channel slices.  Each thread converts its pixel row (TMEM lane) of a slice
+      // and writes the 64 bytes into its group's double-buffered staging tile, laid out like a TMA operand (64 B rows,
+      // 64 B swizzle); one elected thread per group hands the slice to the TMA unit (one bulk tensor store, rows
+      // outside the tensor clipped) and the group goes on.  The residual arrives the same way, two slices ahead --
+      // the first of a tile while its main loop is still running -- so the drain never waits on a global load, and
+      // per-thread 16-byte stores to 128 different rows (one sector each, LSU-bound) are gone.  Requires 128-pixel
+      // tiles, bf16 output, identity output map, Cout % 32 == 0 (host-checked).
+      const int grp = (warp - 4) >> 2, eg = etid & 127;
+      uint8_t* out_stage = smem + a.off_out + grp * (2 * 128 * 64);
+      uint8_t* res_stage = smem + a.off_res + grp * (2 * 128 * 64);
+      uint64_t* rfull = res_full + grp * 2;
       const bool res = a.residual != nullptr;
-      uint32_t sl = 0;  // running slice counter: staging buffer = sl & 1, residual barrier parity = (sl >> 1) & 1
+      const int sw = (row >> 1) & 3;  // 64-byte swizzle: 16-byte unit index ^ address bits [7, 9)
+      uint32_t sl = 0;  // slices this group has drained: staging buffer = sl & 1, residual barrier parity = (sl >> 1) & 1
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_tile = tile / m_tiles;
         const int m_tile = tile % m_tiles;
@@ -252,13 +257,13 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int tb = m_tile / (a.tiles_w * a.tiles_h);
         const int w0 = tw * a.BW, h0 = th * a.BH, b0 = tb * a.BB;
         const int nbase = n_tile * a.block_n;
-        int nsl = (a.Cout - nbase) >> 6;
-        if (nsl > (a.block_n >> 6)) nsl = a.block_n >> 6;
+        int nsl = (a.Cout - nbase) >> 5;
+        if (nsl > (a.block_n >> 5)) nsl = a.block_n >> 5;
         const int bb = row / rows_per_b;
-        if (stage_add) {
-          asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers are done
+        if (stage_add && !(dbg & 32)) {
+          asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's readers are done
           const int total = a.BB * a.block_n;
-          for (int i = etid; i < total; i += 128) {
+          for (int i = etid; i < total; i += 256) {
             const int sb = i / a.block_n, n = nbase + (i - sb * a.block_n);
             float v = 0.f;
             if (n < a.Cout) {
@@ -268,41 +273,53 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             smem_add[i] = v;
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
         }
         const float* addrow = smem_add + (bb < a.BB ? bb : 0) * a.block_n;
-        if (res && etid == 0) {
-          for (int s2 = 0; s2 < 2 && s2 < nsl; ++s2) {
-            const uint32_t buf = (sl + s2) & 1;
-            mbar_expect_tx(&res_full[buf], 128 * 128);
-            tma_load_4d(res_stage + buf * (128 * 128), &tmR, &res_full[buf], nbase + 64 * s2, w0, h0, b0);
+        if (res && eg == 0) {
+          for (int k = 0; k < 2; ++k) {
+            const int s2 = grp + 2 * k;
+            if (s2 < nsl) {
+              const uint32_t buf = (sl + k) & 1;
+              mbar_expect_tx(&rfull[buf], 128 * 64);
+              tma_load_4d(res_stage + buf * (128 * 64), &tmR, &rfull[buf], nbase + 32 * s2, w0, h0, b0);
+            }
           }
         }
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * a.block_n;
-        for (int s2 = 0; s2 < nsl; ++s2, ++sl) {
+        if (grp >= nsl) {  // nothing to drain for this group (32-channel tile): hand the accumulator back at once
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        for (int s2 = grp; s2 < nsl; s2 += 2, ++sl) {
           const uint32_t buf = sl & 1;
-          uint32_t r0[32], r1[32];
-          tmem_ld32(taddr + s2 * 64, r0);
-          tmem_ld32(taddr + s2 * 64 + 32, r1);
-          if (res) mbar_wait(&res_full[buf], (sl >> 1) & 1);
+          uint32_t r0[32];
+          tmem_ld32(taddr + s2 * 32, r0);
+          if (res) mbar_wait(&rfull[buf], (sl >> 1) & 1);
           tmem_ld_wait();
-          uint8_t* orow = out_stage + buf * (128 * 128) + row * 128;
-          const uint8_t* rrow = res_stage + buf * (128 * 128) + row * 128;
+          if (s2 + 2 >= nsl) {  // every TMEM read of this warp has completed: hand the accumulator back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          }
+          uint8_t* orow = out_stage + buf * (128 * 64) + row * 64;
+          const uint8_t* rrow = res_stage + buf * (128 * 64) + row * 64;
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {  // 16-byte units of the row: channels [8u, 8u + 8) of the slice
+          for (int u = 0; u < 4; ++u) {  // 16-byte units of the row: channels [8u, 8u + 8) of the slice
             float v[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(u < 4 ? r0[u * 8 + j] : r1[(u - 4) * 8 + j]);
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r0[u * 8 + j]);
             if (has_add) {
               if (stage_add) {
-                const float4 a0 = *reinterpret_cast<const float4*>(addrow + s2 * 64 + u * 8);
-                const float4 a1 = *reinterpret_cast<const float4*>(addrow + s2 * 64 + u * 8 + 4);
+                const float4 a0 = *reinterpret_cast<const float4*>(addrow + s2 * 32 + u * 8);
+                const float4 a1 = *reinterpret_cast<const float4*>(addrow + s2 * 32 + u * 8 + 4);
                 v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
                 v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
               } else {
-                const int n = nbase + s2 * 64 + u * 8;
+                const int n = nbase + s2 * 32 + u * 8;
                 const int gb = b0 + bb < a.B ? b0 + bb : a.B - 1;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -311,7 +328,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
               }
             }
-            const int su = (u ^ (row & 7)) << 4;
+            const int su = (u ^ sw) << 4;
             if (res) {
               const uint4 rv = *reinterpret_cast<const uint4*>(rrow + su);
               const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
@@ -325,22 +342,17 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             *reinterpret_cast<uint4*>(orow + su) =
                 make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
           }
-          if (s2 + 1 == nsl) {  // every TMEM read of this warp has completed: hand the accumulator back
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-          }
           fence_proxy_async();
-          // the staging buffer the NEXT slice will fill was handed to the TMA unit one slice ago: once that store has
-          // read it (it has had a whole slice of time), everybody may overwrite it after the barrier
-          if (etid == 0) bulk_wait_group_read<0>();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (etid == 0) {
-            tma_store_4d(&tmY, out_stage + buf * (128 * 128), nbase + 64 * s2, w0, h0, b0);
+          // the staging buffer the group's NEXT slice will fill was handed to the TMA unit one slice ago: once that
+          // store has read it (it has had a whole slice of time), the group may overwrite it after the barrier
+          if (eg == 0) bulk_wait_group_read<0>();
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
+          if (eg == 0) {
+            if (!(dbg & 64)) tma_store_4d(&tmY, out_stage + buf * (128 * 64), nbase + 32 * s2, w0, h0, b0);
             bulk_commit_group();
-            if (res && s2 + 2 < nsl) {  // this residual buffer has been read by everyone: refill it two slices ahead
-              mbar_expect_tx(&res_full[buf], 128 * 128);
-              tma_load_4d(res_stage + buf * (128 * 128), &tmR, &res_full[buf], nbase + 64 * (s2 + 2), w0, h0, b0);
+            if (res && s2 + 4 < nsl) {  // this residual buffer has been read by the group: refill it two slices ahead
+              mbar_expect_tx(&rfull[buf], 128 * 64);
+              tma_load_4d(res_stage + buf * (128 * 64), &tmR, &rfull[buf], nbase + 32 * (s2 + 4), w0, h0, b0);
             }
           }
         }
@@ -349,8 +361,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           acc_phase ^= 1;
         }
       }
-      if (etid == 0) bulk_wait_group<0>();
-    } else
+      if (eg == 0) bulk_wait_group<0>();
+    } else if (warp < 8)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
      const int n_tile = tile / m_tiles;
      for (int hf = 0; hf < mt; ++hf) {
@@ -897,9 +909,9 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
   // bulk-tensor epilogue (see the kernel): 2 x 16 KB output staging (+ 2 x 16 KB residual staging)
   a.epi_tma = (!(env_knobs().conv_dbg > 0 && (env_knobs().conv_dbg & 16)) && p->y_dtype == PDDM_BF16 &&
                p->out_sh == 1 && p->out_sw == 1 && p->out_oh == 0 && p->out_ow == 0 && p->out_H == p->H &&
-               p->out_W == p->W && p->Cout % 64 == 0 && a.block_n % 64 == 0 && a.mt == 1 &&
+               p->out_W == p->W && p->Cout % 32 == 0 && a.block_n % 32 == 0 && a.mt == 1 &&
                a.BW * a.BH * a.BB == 128 && (!p->residual || p->res_dtype == PDDM_BF16)) ? 1 : 0;
-  const int epi_bytes = a.epi_tma ? (p->residual ? 4 : 2) * 128 * 128 + 1024 : 0;
+  const int epi_bytes = a.epi_tma ? (p->residual ? 8 : 4) * 128 * 64 + 1024 : 0;  // [group][2] x 8 KB (+ residual)
   const int budget = device_info().max_smem_optin - 1024 - 512 - kAddBytes - epi_bytes;
   int stages = budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -907,7 +919,7 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
   if (stages < 2) return PDDM_ERR_UNSUPPORTED;
   a.stages = stages;
   a.off_out = (static_cast<uint32_t>(stages) * stage_bytes + 512 + kAddBytes + 1023) / 1024 * 1024;
-  a.off_res = a.off_out + 2 * 128 * 128;
+  a.off_res = a.off_out + 4 * 128 * 64;
   const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 + 512 + kAddBytes + epi_bytes;
 
   CUtensorMap tmA, tmA2, tmB;
@@ -945,11 +957,11 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
                               static_cast<uint64_t>(p->B)};
     const uint64_t str[3] = {static_cast<uint64_t>(p->Cout) * 2, static_cast<uint64_t>(p->W) * p->Cout * 2,
                              static_cast<uint64_t>(p->H) * p->W * p->Cout * 2};
-    const uint32_t box[4] = {64, static_cast<uint32_t>(a.BW), static_cast<uint32_t>(a.BH), static_cast<uint32_t>(a.BB)};
-    int rc = make_tmap_bf16(&tmY, p->y, 4, dims, str, box, 128);
+    const uint32_t box[4] = {32, static_cast<uint32_t>(a.BW), static_cast<uint32_t>(a.BH), static_cast<uint32_t>(a.BB)};
+    int rc = make_tmap_bf16(&tmY, p->y, 4, dims, str, box, 64);
     if (rc) return rc;
     tmR = tmY;
-    if (p->residual && (rc = make_tmap_bf16(&tmR, p->residual, 4, dims, str, box, 128))) return rc;
+    if (p->residual && (rc = make_tmap_bf16(&tmR, p->residual, 4, dims, str, box, 64))) return rc;
   }
   if (ensure_smem_optin(reinterpret_cast<const void*>(conv_fwd_kernel))) return PDDM_ERR_CUDA;
   const int total_tiles = ((a.m_tiles + a.mt - 1) / a.mt) * a.n_tiles;

@@ -303,6 +303,9 @@ int main(int argc, char** argv) {
     add3("3x3 8x8 256->256 b128", 128, 8, 8, 256, 256, 1, 1, -1, PDDM_BF16);
     add3("3x3 4x4 256->256 b128", 128, 4, 4, 256, 256, 1, 1, -1, PDDM_BF16);
     add1("1x1 16x16 256->768 b128", 128, 16, 16, 256, 256, 0, 768, PDDM_BF16);
+    add1("1x1 16x16 256->256 b128", 128, 16, 16, 256, 256, 0, 256, PDDM_BF16);
+    add1("1x1 32x32 256->128 b128", 128, 32, 32, 256, 256, 0, 128, PDDM_BF16);
+    add3("3x3 16x16 256->256 b128 +res", 128, 16, 16, 256, 256, 1, 1, PDDM_BF16, PDDM_BF16);
   }
   int fails = 0;
   for (auto& c : cases) fails += run_case(c);
