@@ -276,15 +276,18 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           asm volatile("bar.sync 1, 256;" ::: "memory");
         }
         const float* addrow = smem_add + (bb < a.BB ? bb : 0) * a.block_n;
-        if (res && eg == 0) {
-          for (int k = 0; k < 2; ++k) {
-            const int s2 = grp + 2 * k;
-            if (s2 < nsl) {
-              const uint32_t buf = (sl + k) & 1;
-              mbar_expect_tx(&rfull[buf], 128 * 64);
-              tma_load_4d(res_stage + buf * (128 * 64), &tmR, &rfull[buf], nbase + 32 * s2, w0, h0, b0);
+        if (res && q == 0) {
+          if (elect_one()) {
+            for (int k = 0; k < 2; ++k) {
+              const int s2 = grp + 2 * k;
+              if (s2 < nsl) {
+                const uint32_t buf = (sl + k) & 1;
+                mbar_expect_tx(&rfull[buf], 128 * 64);
+                tma_load_4d(res_stage + buf * (128 * 64), &tmR, &rfull[buf], nbase + 32 * s2, w0, h0, b0);
+              }
             }
           }
+          __syncwarp();
         }
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
@@ -343,17 +346,25 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
           }
           fence_proxy_async();
-          // the staging buffer the group's NEXT slice will fill was handed to the TMA unit one slice ago: once that
-          // store has read it (it has had a whole slice of time), the group may overwrite it after the barrier
-          if (eg == 0) bulk_wait_group_read<0>();
+          // The staging buffer the group's NEXT slice will fill was handed to the TMA unit one slice ago by the warp
+          // whose turn it was: once that store has read it (it has had a whole slice of time), the group may overwrite
+          // it after the barrier.  The issuing role rotates over the group's four warps and is taken by an elected
+          // lane in warp-uniform code, so the ~300 cycles of TMA issue land on a different warp every slice.
+          if (q == ((sl + 3) & 3)) {
+            if (elect_one()) bulk_wait_group_read<0>();
+            __syncwarp();
+          }
           asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
-          if (eg == 0) {
-            if (!(dbg & 64)) tma_store_4d(&tmY, out_stage + buf * (128 * 64), nbase + 32 * s2, w0, h0, b0);
-            bulk_commit_group();
-            if (res && s2 + 4 < nsl) {  // this residual buffer has been read by the group: refill it two slices ahead
-              mbar_expect_tx(&rfull[buf], 128 * 64);
-              tma_load_4d(res_stage + buf * (128 * 64), &tmR, &rfull[buf], nbase + 32 * (s2 + 4), w0, h0, b0);
+          if (q == (sl & 3)) {
+            if (elect_one()) {
+              if (!(dbg & 64)) tma_store_4d(&tmY, out_stage + buf * (128 * 64), nbase + 32 * s2, w0, h0, b0);
+              bulk_commit_group();
+              if (res && s2 + 4 < nsl) {  // this residual buffer has been read by the group: refill it two slices ahead
+                mbar_expect_tx(&rfull[buf], 128 * 64);
+                tma_load_4d(res_stage + buf * (128 * 64), &tmR, &rfull[buf], nbase + 32 * (s2 + 4), w0, h0, b0);
+              }
             }
+            __syncwarp();
           }
         }
         if (++acc == nacc) {
@@ -361,7 +372,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           acc_phase ^= 1;
         }
       }
-      if (eg == 0) bulk_wait_group<0>();
+      if (elect_one()) bulk_wait_group<0>();  // every warp's issuing lane: its stores have completed
+      __syncwarp();
     } else if (warp < 8)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
      const int n_tile = tile / m_tiles;
