@@ -21,11 +21,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "train img/s (+ 1000-step samples/s), CIFAR-10 32x32 improved-diffusion UNet"
-MODEL = "unet"
-RES = 32
-PER_GPU_BATCH = 128
-CPU_BATCH = 16
+# --config: BASELINE.json configs[1] (default; the configuration the metric is quoted on) and configs[4]
+CONFIGS = {
+    "cifar": dict(model="unet", res=32, batch=128,
+                  metric="train img/s (+ 1000-step samples/s), CIFAR-10 32x32 improved-diffusion UNet",
+                  workload="BASELINE configs[1]: CIFAR-10-shape 3x32x32 UNet (config/model/unet.yaml), cosine "
+                           "schedule, learned variance, L_hybrid, Adam, bf16 compute / fp32 accumulate"),
+    "celeba64": dict(model="unet_celeba", res=64, batch=64,
+                     metric="train img/s (+ 1000-step samples/s), CelebA 64x64 UNet with attention at 16x16 / 8x8",
+                     workload="BASELINE configs[4]: CelebA-shape 3x64x64 UNet (config/model/unet_celeba.yaml), cosine "
+                              "schedule, learned variance, L_hybrid, Adam, bf16 compute / fp32 accumulate"),
+}
+METRIC, MODEL, RES, PER_GPU_BATCH = (CONFIGS["cifar"][k] for k in ("metric", "model", "res", "batch"))
 
 
 def peaks():
@@ -49,7 +56,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -86,23 +93,29 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# forward 3x3 conv census of config/model/unet.yaml at 32x32: (H, Cin, Cout, count)
-CONV_CENSUS = [(32, 128, 128, 10), (16, 256, 256, 10), (16, 512, 256, 3), (32, 256, 128, 3), (32, 256, 256, 1),
-               (32, 384, 128, 1), (8, 256, 256, 11), (8, 512, 256, 4), (16, 384, 256, 1), (4, 256, 256, 14),
-               (4, 512, 256, 4)]
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed summary of
+    an ``ncu --set full`` capture on this tree (profiles/r2_conv_fwd_ncu_traffic.json); None if no capture exists."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_conv_fwd_ncu_traffic.json")) as f:
+            t = json.load(f)
+        return float(t["dram_bytes_per_launch"]), t.get("note", "")
+    except Exception:
+        return None, "no ncu --set full capture of this kernel committed for this tree"
 
 
-def dominant_kernel_roofline(dev, B, burst_tflops, src):
+def dominant_kernel_roofline(dev, B, burst_tflops, src, census):
     """Time the dominant kernel (conv_fwd_kernel: the tcgen05 tap-GEMM behind every conv forward and data gradient)
-    live with CUDA events on the model's own 3x3 conv census: one launch per layer, distinct input/weight tensors per
-    layer (0.6 GB of operands, > L2).  achieved = algorithmic FLOPs of the census / time of the census."""
+    live with CUDA events on the model's own 3x3 conv census (configs.conv3x3_census; stride-2 convs counted at their
+    output resolution): one launch per layer, distinct input/weight tensors per layer (> L2 in total).
+    achieved = algorithmic FLOPs of the census / time of the census."""
     import torch
 
     from probabilisticdeepdiffusionmodels_b200 import _lib, ops
     P = torch.ops.pddm
     g = torch.Generator(device=dev).manual_seed(0)
     layers, flops = [], 0.0
-    for H, cin, cout, count in CONV_CENSUS:
+    for H, cin, cout, count in census:
         for _ in range(count):
             x = torch.randn((B, H, H, cin), generator=g, device=dev).to(torch.bfloat16)
             w = torch.randn((cout, cin, 3, 3), generator=g, device=dev) * 0.02
@@ -133,17 +146,16 @@ def dominant_kernel_roofline(dev, B, burst_tflops, src):
         torch.cuda.synchronize(dev)
     sec = e0.elapsed_time(e1) * 1e-3 / reps
     ach = flops / sec / 1e12
+    traffic, note = measured_traffic()
     return {"bound": "tensor", "achieved": ach, "peak": burst_tflops, "unit": "TFLOP/s", "frac": ach / burst_tflops,
-            # dram__bytes_read+write of one 32x32 128->128 launch from the ncu --set full capture in profiles/
-            "traffic": 34.04e6, "traffic_note": "per launch of the 3x3 32x32 128->128 B=128 layer (algorithmic: 67 MB; "
-                                                "the output stays in L2 during the capture)",
+            "traffic": traffic, "traffic_note": note,
             "kernel": "pddm::conv_fwd_kernel (conv_fwd_swap_kernel, its swapped-operand variant, for <=128 output channels)",
             "launches_timed": int(launches), "us_per_launch": sec / launches * 1e6,
             "flops_per_census": flops, "peak_source": f"{src} (burst bf16, kernel timed alone)",
-            "workload": "forward 3x3 conv census of the CIFAR UNet at B=128 (62 launches), CUDA events"}
+            "workload": f"forward 3x3 conv census of the {MODEL} model at B={B} ({int(launches)} launches), CUDA events"}
 
 
-def cpu_reference_arm(steps, warmup, batch=CPU_BATCH, threads=None):
+def cpu_reference_arm(steps, warmup, batch=None, threads=None):
     """The reference's own PyTorch path (CPU oracle port, fp32): training step with Adam + a few reverse steps."""
     import numpy as np
     import torch
@@ -152,6 +164,7 @@ def cpu_reference_arm(steps, warmup, batch=CPU_BATCH, threads=None):
     from oracle.diffusion_ref import DiffusionRef
     from oracle.unet_ref import MODEL_CONFIGS, arch_from_config, make_params
 
+    batch = batch or PER_GPU_BATCH
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
     cfg = MODEL_CONFIGS[MODEL]
@@ -193,6 +206,67 @@ def cpu_reference_arm(steps, warmup, batch=CPU_BATCH, threads=None):
                       f"sampling = {nst} reverse steps at B={batch} extrapolated x1000/{nst} to 1000-step chains"}
 
 
+def micro_diffusion():
+    """HBM evidence for the fused elementwise diffusion kernels (north_star group 4): time
+    q_sample / p_sample / vlb / sq_err at the training batch (B=128: 1.5 MB tensors, launch-bound) and at a
+    bandwidth-meaningful size (B=16384: 201 MB tensors, > L2), 20 launches in a CUDA graph, CUDA events; GB/s =
+    algorithmic bytes (every fp32 tensor read or written once) / time, against the measured HBM peak."""
+    import torch
+
+    from probabilisticdeepdiffusionmodels_b200 import functional as F
+    from probabilisticdeepdiffusionmodels_b200 import schedules
+    burst, sustained, hbm, src = peaks()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    tabs = F.DeviceTables(schedules.make_tables(schedules.get_betas(diffusion_steps=1000, mode="cosine").float()), dev)
+    out = {"metric": "GB/s of the fused diffusion kernels (fp32, 3x32x32 images)", "unit": "GB/s", "peak": hbm,
+           "peak_source": src, "n_gpus": 1, "dtype": "f32", "data": "synthetic", "kernels": {}}
+    g = torch.Generator(device=dev).manual_seed(0)
+    for B in (128, 16384):
+        x0 = torch.rand((B, 3, 32, 32), generator=g, device=dev) * 2 - 1
+        noise = torch.randn((B, 3, 32, 32), generator=g, device=dev)
+        t = torch.randint(1, 1001, (B,), generator=g, device=dev)
+        mo = torch.randn((B, 6, 32, 32), generator=g, device=dev)  # eps | v (learned variance)
+        z = torch.randn((B, 3, 32, 32), generator=g, device=dev)
+        mo3 = mo[:, :3].contiguous()
+        x_t = F.q_sample(x0, noise, t, tabs)
+        gsc = torch.ones(B, device=dev)
+        n = x0.numel() * 4  # bytes of one [B, 3, 32, 32] fp32 tensor
+        cases = {
+            "q_sample": (lambda: F.q_sample(x0, noise, t, tabs), 3 * n),                        # x0, noise -> x_t
+            "p_sample(learned sigma)": (lambda: F.p_sample_step(x_t, mo, z, 500, tabs, True, "learned"), 5 * n),
+            "p_sample(fixed sigma)": (lambda: F.p_sample_step(x_t, mo3, z, 500, tabs, True, "beta"), 4 * n),
+            "vlb(L_vlb, learned sigma, +grad_v)": (lambda: F.vlb_terms(x0, x_t, mo, t, tabs, 1, "learned", True), 5 * n),
+            "sq_err(+grad)": (lambda: F.sq_err(mo, noise, gsc, True), 5 * n),                  # pred(6ch), noise -> grad(6ch)
+        }
+        for name, (fn, nbytes) in cases.items():
+            try:
+                fn()
+            except Exception as e:  # a sigma mode this build does not name the same way: report, do not die
+                out["kernels"][f"{name} B={B}"] = {"error": str(e)[:80]}
+                continue
+            s_ = torch.cuda.Stream(dev)
+            with torch.cuda.stream(s_):
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr, stream=s_):
+                    for _ in range(20):
+                        fn()
+                gr.replay()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(s_)
+                for _ in range(3):
+                    gr.replay()
+                e1.record(s_)
+            e1.synchronize()
+            us = e0.elapsed_time(e1) / 60 * 1e3
+            gbs = nbytes / us * 1e-3
+            out["kernels"][f"{name} B={B}"] = {"us": round(us, 2), "GB/s": round(gbs, 1), "frac": round(gbs / hbm, 3),
+                                              "bytes": nbytes}
+    best = max((v.get("GB/s", 0) for v in out["kernels"].values()), default=0)
+    out["value"] = best
+    print(json.dumps(out), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -201,7 +275,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--bucketed-allreduce", action="store_true",
                     help="N>1: all-reduce bucket by bucket from inside backward on a communication stream")
-    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--config", default="cifar", choices=sorted(CONFIGS),
+                    help="cifar = BASELINE configs[1] (the metric's configuration); celeba64 = configs[4]")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch images per GPU; strong: --batch images in total, split over the GPUs")
+    ap.add_argument("--micro", default=None, choices=["diffusion"],
+                    help="diffusion: GB/s of the fused q_sample / p_sample / vlb / sq_err kernels instead of the step")
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (weak) / global batch (strong)")
     ap.add_argument("--sample-steps", type=int, default=1000, help="length of the timed reverse chain")
     ap.add_argument("--no-sampling", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -209,22 +289,39 @@ def main():
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    global METRIC, MODEL, RES, PER_GPU_BATCH
+    METRIC, MODEL, RES = (CONFIGS[args.config][k] for k in ("metric", "model", "res"))
+    if args.batch is None:
+        args.batch = CONFIGS[args.config]["batch"]
+    if args.scaling == "strong":
+        if args.batch % max(world, 1):
+            raise SystemExit("--scaling strong: the global batch must divide by the number of GPUs")
+        global_batch, args.batch = args.batch, args.batch // max(world, 1)
+    else:
+        global_batch = args.batch * max(world, 1)
+    PER_GPU_BATCH = args.batch
 
-    cfg_json = {"workload": "BASELINE configs[1]: CIFAR-10-shape 3x32x32 UNet (config/model/unet.yaml), cosine "
-                            "schedule, learned variance, L_hybrid, Adam, bf16 compute / fp32 accumulate",
-                "per_gpu_batch": args.batch, "global_batch": args.batch * max(world, 1), "parallelism": f"dp{world}",
+    cfg_json = {"workload": CONFIGS[args.config]["workload"],
+                "per_gpu_batch": args.batch, "global_batch": global_batch, "parallelism": f"dp{world}",
                 "l2_policy": "activations + weights + grads per step (>2 GB) exceed the 126 MB L2; no explicit flush"}
+
+    if args.micro == "diffusion":
+        if rank == 0:
+            micro_diffusion()
+        return
 
     if args.impl == "reference":
         if rank != 0:
             return
-        steps = max(1, min(args.steps, 5))
+        # the reference's CPU path on the SAME configuration (batch included); every step is a whole batch, the
+        # run is bounded by timing at most 3 steps (~4 s each at B=128 on 16 host threads)
+        steps = max(1, min(args.steps, 3))
         warm = max(1, min(args.warmup, 1))
-        r = cpu_reference_arm(steps, warm)
+        r = cpu_reference_arm(steps, warm, batch=args.batch)
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": r["train_img_s"], "unit": "img/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg_json,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg_json,
             "sampling": {"value": r["samples_s"], "unit": "samples/s (1000-step chains)",
                          "image_steps_per_s": r["image_steps_s"]},
             "cpu_baseline": {"value": r["train_img_s"], "unit": "img/s", "cores": r["cores"], "kind": "port",
@@ -238,7 +335,8 @@ def main():
     # (nothing on this arm imports oracle/: configurations, the synthetic initialisation and the FLOP counter
     #  live in the package; the oracle is only executed by the cpu_baseline / --impl reference leg above)
     from probabilisticdeepdiffusionmodels_b200 import Engine, _lib, parallel
-    from probabilisticdeepdiffusionmodels_b200.configs import MODEL_CONFIGS, synthetic_init_, unet_fwd_flops_per_image
+    from probabilisticdeepdiffusionmodels_b200.configs import (MODEL_CONFIGS, conv3x3_census, synthetic_init_,
+                                                               unet_fwd_flops_per_image)
 
     rank, world, local_rank = parallel.init_from_env("nccl")
     dev = torch.device("cuda", local_rank)
@@ -249,6 +347,7 @@ def main():
                  clip_while_generating=True, learn_sigma=True, log_loss_per_t=False)
     synthetic_init_(eng.model, seed=1)  # random init incl. the reference's zero-init convs
     fwd_flops = unet_fwd_flops_per_image(eng.model, RES)
+    census = conv3x3_census(eng.model, RES)
     eng = eng.to(dev)
     parallel.broadcast_parameters(eng.model)
     B = args.batch
@@ -369,20 +468,20 @@ def main():
     roof_step = {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
                  "frac": achieved / sustained, "peak_source": f"{src} (sustained bf16; burst {burst})",
                  "scope": "whole train step per GPU (algorithmic 3 x fwd FLOPs/img x img/s)"}
-    roof = dominant_kernel_roofline(dev, B, burst, src)
+    roof = dominant_kernel_roofline(dev, B, burst, src, census)
     if sampling is not None:
         s_ach = sampling["image_steps_per_s"] / world * fwd / 1e12
         sampling["roofline_frac"] = s_ach / sustained
         sampling["achieved_tflops_per_gpu"] = s_ach
     line = {"metric": METRIC, "value": img_s, "unit": "img/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg_json, "clocks": clk.summary(),
             "e2e": {"value": img_s_e2e, "unit": "img/s", "h2d_bytes_per_step": host_x.numel() * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e, "last_loss": loss_val},
             "gpu_launches": int(kernels_per_step * args.steps), "kernels_per_step": int(kernels_per_step),
             "roofline": roof, "roofline_step": roof_step, "sampling": sampling}
     if not args.no_cpu_baseline and world == 1:
-        r = cpu_reference_arm(2, 1)
+        r = cpu_reference_arm(2, 1, batch=min(B, 32))
         line["cpu_baseline"] = {"value": r["train_img_s"], "unit": "img/s", "cores": r["cores"], "kind": "port",
                                 "sample": r["sample"], "samples_per_s": r["samples_s"]}
     print(json.dumps(line), flush=True)

@@ -88,3 +88,30 @@ def unet_fwd_flops_per_image(model, resolution):
             total += f
     total += conv_fl(model.out[2], r)
     return total
+
+
+def conv3x3_census(model, resolution):
+    """The model's forward 3x3 convolutions (stride 1 and 2, stem / head excluded: they run thin-GEMM paths) as
+    ``[(H_out, Cin, Cout, count)]`` -- the workload of the dominant tap-GEMM kernel."""
+    from collections import OrderedDict
+
+    from .unet import Downsample, ResBlock, Upsample
+    census = OrderedDict()
+
+    def add(r, conv):
+        key = (r, conv.in_channels, conv.out_channels)
+        census[key] = census.get(key, 0) + 1
+
+    r = resolution
+    for seq in list(model.input_blocks)[1:] + [model.middle_block] + list(model.output_blocks):
+        for mod in seq:
+            if isinstance(mod, ResBlock):
+                add(r, mod.in_layers[2])
+                add(r, mod.out_layers[3])
+            elif isinstance(mod, Downsample):
+                r = (r + 1) // 2
+                add(r, mod.op)
+            elif isinstance(mod, Upsample):
+                r = 2 * r
+                add(r, mod.conv)
+    return [(k[0], k[1], k[2], n) for k, n in census.items()]

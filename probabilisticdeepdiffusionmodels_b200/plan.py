@@ -570,6 +570,9 @@ class _ResNode:
         B = plan.B
         plan._need_wgrad_ws(B, H, W, self.cin, self.cout, 9)
         plan._need_wgrad_ws(B, H, W, self.cout, self.cout, 9)
+        if self.sk is not None:  # the 1x1 skip conv: whole input, or its two sources one after the other
+            for c_ in {self.cin, cin_a, cin_b} - {0}:
+                plan._need_wgrad_ws(B, H, W, c_, self.cout, 1)
         # can the two-source input stay un-concatenated?  (GroupNorm chunks must not straddle the seam)
         self.two_src = cin_b > 0 and F.gn_pipe_slots(B, H * W, self.cin, self.n1.num_groups, cin_a, 1) >= 2 and \
             cin_a % (64 if self.cin % 64 == 0 else 32) == 0
@@ -635,6 +638,7 @@ class _AttnNode:
         plan._small(mod.qkv.bias, self.q_cs)
         plan._small(mod.proj_out.bias, self.out_cs)
         plan._need_wgrad_ws(plan.B, H, W, self.C, 3 * self.C, 1)
+        plan._need_wgrad_ws(plan.B, H, W, self.C, self.C, 1)
 
     def fwd(self, x, _skip, S):
         pl, B, H, W, Cc = self.plan, self.plan.B, self.H, self.W, self.C
