@@ -175,6 +175,10 @@ int pddm_convert(const void* x, int32_t x_dtype, void* y, int32_t y_dtype, int64
 /* SiLU on an fp32 vector -> out dtype; and its backward (dx = dy * silu'(x)).  (src/modules/nn.py:13-15) */
 int pddm_silu(const float* x, void* y, int32_t y_dtype, int64_t n, pddm_stream_t stream);
 int pddm_silu_bwd(const float* x, const float* dy, float* dx, int64_t n, pddm_stream_t stream);
+/* SiLU on a bf16 feature map (n elements, n % 8 == 0, 16-byte aligned) and its backward -- the reference's stand-alone
+ * nn.SiLU between GroupNorm and conv (src/modules/unet.py:146-150, 163-166) for models assembled from the nn.py seam. */
+int pddm_silu_map(const void* x, void* y, int64_t n, pddm_stream_t stream);
+int pddm_silu_map_bwd(const void* x, const void* dy, void* dx, int64_t n, pddm_stream_t stream);
 /* Column sums, deterministic (two-stage, fixed summation order; no atomics).  workspace: pddm_colsum_workspace bytes
  * for (rows per segment, segments, C) -- (M, 1, C) for pddm_colsum, (HW, B, C) for the per-sample variant.
  * out[c] (+)= sum_m x[m, c]  (x bf16 [M, ld], fp32 out [C]); used for conv bias gradients. */

@@ -175,6 +175,40 @@ __global__ void silu_bwd_kernel(const float* __restrict__ x, const float* __rest
   }
 }
 
+// SiLU on bf16 feature maps (the reference's stand-alone nn.SiLU between GroupNorm and conv, src/modules/unet.py:146-150;
+// this framework's own UNet fuses it into GroupNorm): 8 values per thread, fp32 math.  n8 = number of 16-byte groups.
+__global__ void silu_map_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, long long n8) {
+  pdl_entry();
+  GRID_STRIDE(i, n8) {
+    uint4 v = x[i];
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 f = __bfloat1622float2(h[k]);
+      f.x = f.x / (1.f + __expf(-f.x));
+      f.y = f.y / (1.f + __expf(-f.y));
+      h[k] = __floats2bfloat162_rn(f.x, f.y);
+    }
+    y[i] = v;
+  }
+}
+__global__ void silu_map_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, uint4* __restrict__ dx,
+                                    long long n8) {
+  pdl_entry();
+  GRID_STRIDE(i, n8) {
+    uint4 v = x[i], g = dy[i];
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+    const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&g);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __bfloat1622float2(h[k]), d = __bfloat1622float2(gh[k]);
+      const float s0 = 1.f / (1.f + __expf(-f.x)), s1 = 1.f / (1.f + __expf(-f.y));
+      h[k] = __floats2bfloat162_rn(d.x * s0 * (1.f + f.x * (1.f - s0)), d.y * s1 * (1.f + f.y * (1.f - s1)));
+    }
+    dx[i] = v;
+  }
+}
+
 // ---------------------------------------------------------------------------------- dtype conversion
 template <typename TI, typename TO>
 __global__ void convert_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long n) {
@@ -554,6 +588,20 @@ extern "C" int pddm_convert(const void* x, int32_t x_dtype, void* y, int32_t y_d
 extern "C" int pddm_silu(const float* x, void* y, int32_t y_dtype, int64_t n, pddm_stream_t s) {
   if (!x || !y || n <= 0) return PDDM_ERR_BAD_ARG;
   PdlLaunch(grid_for(n, 256), 256, 0, S(s))(silu_kernel, x, y, y_dtype, n);
+  return launch_status();
+}
+extern "C" int pddm_silu_map(const void* x, void* y, int64_t n, pddm_stream_t s) {
+  if (!x || !y || n <= 0 || n % 8 != 0 || !aligned16(x) || !aligned16(y)) return PDDM_ERR_BAD_ARG;
+  PdlLaunch(grid_for(n / 8, 256), 256, 0, S(s))(silu_map_kernel, static_cast<const uint4*>(x), static_cast<uint4*>(y),
+                                                static_cast<long long>(n / 8));
+  return launch_status();
+}
+extern "C" int pddm_silu_map_bwd(const void* x, const void* dy, void* dx, int64_t n, pddm_stream_t s) {
+  if (!x || !dy || !dx || n <= 0 || n % 8 != 0 || !aligned16(x) || !aligned16(dy) || !aligned16(dx))
+    return PDDM_ERR_BAD_ARG;
+  PdlLaunch(grid_for(n / 8, 256), 256, 0, S(s))(silu_map_bwd_kernel, static_cast<const uint4*>(x),
+                                                static_cast<const uint4*>(dy), static_cast<uint4*>(dx),
+                                                static_cast<long long>(n / 8));
   return launch_status();
 }
 extern "C" int pddm_silu_bwd(const float* x, const float* dy, float* dx, int64_t n, pddm_stream_t s) {

@@ -314,6 +314,20 @@ def silu_vec_bwd(x, dy):
     return dx
 
 
+def silu_map(x):
+    """SiLU on a contiguous bf16 feature map (any shape, numel % 8 == 0)."""
+    L.require_device(x)
+    y = torch.empty_like(x)
+    L.call("pddm_silu_map", L.ptr(_chk(x, bf16)), L.ptr(y), C.c_int64(x.numel()), L.stream())
+    return y
+
+
+def silu_map_bwd(x, dy):
+    dx = torch.empty_like(x)
+    L.call("pddm_silu_map_bwd", L.ptr(_chk(x, bf16)), L.ptr(_chk(dy, bf16)), L.ptr(dx), C.c_int64(x.numel()), L.stream())
+    return dx
+
+
 def timestep_embedding(t, dim, max_period=10000, dtype=bf16):
     """src/modules/nn.py:104-122; t int64 or float32 [B]."""
     L.require_device(t)

@@ -38,14 +38,22 @@ def as_nchw_view(y, like):
 
 
 class SiLU(nn.Module):
-    """src/modules/nn.py:13-15.  Inside ``unet.py`` SiLU is always fused into the GroupNorm kernel; this stand-alone
-    module only sees the small fp32 embedding vectors."""
+    """src/modules/nn.py:13-15.  Inside this package's ``unet.py`` SiLU is always fused into the GroupNorm kernel;
+    the stand-alone module serves models assembled from these factories the way the reference's own unet.py does
+    (``Sequential(normalization, SiLU, conv)``, src/modules/unet.py:146-150): fp32 [B, N] embedding vectors and
+    feature maps (logical NCHW / [B, C, T] views of NHWC bf16 storage, or fp32 NCHW which is converted once)."""
 
     def forward(self, x):
         if x.dtype == torch.float32 and x.dim() == 2:
             return P.silu_vec(x.contiguous())
-        raise RuntimeError("stand-alone SiLU on feature maps is fused into GroupNorm32 in this framework "
-                           "(GroupNorm32.forward(x, silu=True)); only [B, N] fp32 embedding vectors are accepted here")
+        if x.dim() == 2:
+            return P.silu_vec(x.float().contiguous())
+        if x.dim() not in (3, 4):
+            raise RuntimeError(f"SiLU: unsupported input rank {x.dim()}")
+        h = as_nhwc(x)
+        if not h.is_contiguous():
+            h = h.contiguous()
+        return as_nchw_view(P.silu_map(h), x)
 
 
 class GroupNorm32(nn.GroupNorm):
@@ -61,6 +69,12 @@ class Conv2d(nn.Conv2d):
         if self.kernel_size not in ((3, 3), (1, 1)) or self.stride not in ((1, 1), (2, 2)) or \
                 self.padding != ((self.kernel_size[0] - 1) // 2,) * 2:
             raise ValueError(f"unsupported conv geometry k={self.kernel_size} s={self.stride} p={self.padding}")
+        if self.kernel_size == (3, 3) and self.stride == (1, 1):
+            # thin convolutions take the dedicated paths the UNet itself uses for its stem and head
+            if self.in_channels <= 4 and x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous():
+                return as_nchw_view(P.stem_conv(x, self.weight, self.bias)[0], x)
+            if self.out_channels <= 8:
+                return P.head_conv(as_nhwc(x), self.weight, self.bias)  # fp32 NCHW, like the model output
         y, _ = P.conv2d(as_nhwc(x), self.weight, self.bias, None, None, self.stride[0], False)
         return as_nchw_view(y, x)
 

@@ -473,6 +473,33 @@ def _gn_backward(ctx, dy, _dm, _dr):
 torch.library.register_autograd("pddm::gn_silu", _gn_backward, setup_context=_gn_setup)
 
 
+# ================================================================================================ silu on feature maps
+@torch.library.custom_op("pddm::silu_map", mutates_args=())
+def silu_map(x: Tensor) -> Tensor:
+    """Stand-alone SiLU on a contiguous bf16 feature map (src/modules/nn.py:13-15 used as in unet.py:146-150)."""
+    return F.silu_map(x)
+
+
+@silu_map.register_fake
+def _(x):
+    return torch.empty_like(x)
+
+
+@torch.library.custom_op("pddm::silu_map_bwd", mutates_args=())
+def silu_map_bwd(x: Tensor, dy: Tensor) -> Tensor:
+    return F.silu_map_bwd(x, dy.contiguous())
+
+
+@silu_map_bwd.register_fake
+def _(x, dy):
+    return torch.empty_like(x)
+
+
+torch.library.register_autograd(
+    "pddm::silu_map", lambda ctx, dy: torch.ops.pddm.silu_map_bwd(ctx.saved_tensors[0], dy),
+    setup_context=lambda ctx, inputs, output: ctx.save_for_backward(inputs[0]))
+
+
 # ================================================================================================ attention
 @torch.library.custom_op("pddm::attention", mutates_args=())
 def attention(qkv: Tensor, heads: int) -> Tuple[Tensor, Tensor]:

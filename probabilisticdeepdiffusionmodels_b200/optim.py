@@ -50,6 +50,35 @@ class FusedAdam(torch.optim.Optimizer):
             st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
         return st
 
+    # ---- checkpoint / resume: the step count lives on the device; state_dict() carries it per parameter as ``step``
+    # (torch.optim.Adam's own format, so the two optimizers' checkpoints are interchangeable) and load_state_dict()
+    # restores it -- bias correction resumes where it stopped instead of restarting at step 1.
+    def state_dict(self):
+        step = float(int(self._step_dev.item())) if self._step_dev is not None else 0.0
+        for group in self.param_groups:
+            for p in group["params"]:
+                st = self.state.get(p)
+                if st:
+                    st["step"] = torch.tensor(step)
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        step = 0
+        for st in self.state.values():
+            if "step" in st:
+                step = max(step, int(float(st["step"])))
+        ps = [p for g in self.param_groups for p in g["params"]]
+        if ps and ps[0].is_cuda:
+            self._step_dev = torch.full((1,), step, dtype=torch.int32, device=ps[0].device)
+        else:
+            self._step_dev = None
+            self._resume_step = step
+        for st in self.state.values():  # the kernel wants contiguous fp32 moments on the parameter's device
+            for k in ("exp_avg", "exp_avg_sq"):
+                if k in st:
+                    st[k] = st[k].float().contiguous()
+
     def flush_tables(self):
         """Upload the pointer tables recorded by ``step()`` calls made under CUDA-graph capture (call after capture)."""
         for table, raw in self._pending:
@@ -68,7 +97,7 @@ class FusedAdam(torch.optim.Optimizer):
             dev = ps[0].device
             L.require_device(ps[0])
             if self._step_dev is None:
-                self._step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+                self._step_dev = torch.full((1,), int(getattr(self, "_resume_step", 0)), dtype=torch.int32, device=dev)
             if not stepped:
                 L.call("pddm_counter_add", L.ptr(self._step_dev), 1, L.stream())
                 stepped = True

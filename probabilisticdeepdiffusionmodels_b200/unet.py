@@ -271,7 +271,12 @@ class UNetModel(nn.Module):
 
     def _emb_ctx(self, act):
         """All ResBlock ``emb_layers`` share the input SiLU(emb) (unet.py:151-157): one [B, 4mc] x [sum Cout, 4mc]^T GEMM."""
-        if not self.batch_emb_projections or self.use_checkpoint:
+        if self.use_checkpoint:
+            # activation checkpointing re-runs each block from its *tensor* inputs (nn.CheckpointFunction detaches and
+            # re-requires grad on them): hand the blocks the plain SiLU(emb) tensor so that the embedding gradient
+            # flows through the checkpoint like in the reference (src/modules/unet.py:160-161)
+            return act
+        if not self.batch_emb_projections:
             return EmbCtx(act)
         blocks = [m for m in self.modules() if isinstance(m, ResBlock)]
         w_all = torch.cat([m.emb_layers[1].weight for m in blocks], dim=0)
