@@ -387,6 +387,12 @@ int pddm_nchw_to_nhwc_padded(const float* src, void* dst, int32_t B, int32_t C, 
                              pddm_stream_t stream);
 int pddm_nhwc_slice_to_nchw(const float* src, float* dst, int32_t B, int32_t C, int32_t HW, int32_t ld,
                             pddm_stream_t stream);
+/* Sample post-processing in one pass (replaces src/modules/fid_score.py:15-27 + src/datasets/data.py:108-128 on the
+ * host): out[b, hw, c] = uint8(255 * clip(x[b, c, hw] * std[c] + mean[c], 0, 1)); mean/std (device, double [C]) may both
+ * be NULL (= the reference's unnormalize(normalize=None, clip=True)).  Double arithmetic and truncation reproduce the
+ * reference's numpy expression bit for bit. */
+int pddm_images_to_uint8(const float* x_nchw, uint8_t* out_nhwc, int32_t B, int32_t C, int32_t HW, const double* mean,
+                         const double* stdv, pddm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * QKVAttention (src/modules/unet.py:237-256): per (sample, head), softmax_fp32((q*s)(k*s)^T) v, s = d^-1/4.

@@ -132,6 +132,7 @@ SIGNATURES = {
     "pddm_convert": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i64, c_vp]),
     "pddm_silu": (c_i32, [c_vp, c_vp, c_i32, c_i64, c_vp]),
     "pddm_silu_bwd": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "pddm_images_to_uint8": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "pddm_silu_map": (c_i32, [c_vp, c_vp, c_i64, c_vp]),
     "pddm_silu_map_bwd": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "pddm_colsum_workspace": (C.c_size_t, [c_i64, c_i32, c_i32]),

@@ -739,6 +739,33 @@ extern "C" int pddm_nchw_to_nhwc_padded(const float* src, void* dst, int32_t B, 
       src, static_cast<bf16*>(dst), B, C, HW, Cp);
   return launch_status();
 }
+// Sample post-processing (src/modules/fid_score.py:15-27 -> src/datasets/data.py:108-128 unnormalize(clip=True) ->
+// the image writer's (255 * A).astype(uint8)): fp32 NCHW model-space samples -> uint8 NHWC pixels in ONE pass, so a
+// mini-batch leaves the device as B*H*W*C bytes instead of 4x that in fp32.  The affine runs in double like the
+// reference's numpy expression (float32 image x float64 std/mean arrays), truncation like astype(uint8).
+__global__ void images_to_uint8_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, int B, int Cc, int HW,
+                                       const double* __restrict__ mean, const double* __restrict__ stdv) {
+  pdl_entry();
+  const long long n = static_cast<long long>(B) * HW * Cc;
+  GRID_STRIDE(i, n) {  // i indexes the NHWC output
+    const int c = static_cast<int>(i % Cc);
+    const long long p = i / Cc;
+    const int hw = static_cast<int>(p % HW);
+    const long long b = p / HW;
+    double v = static_cast<double>(x[(b * Cc + c) * HW + hw]);
+    if (mean) v = v * stdv[c] + mean[c];
+    v = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
+    out[i] = static_cast<uint8_t>(255.0 * v);
+  }
+}
+extern "C" int pddm_images_to_uint8(const float* x_nchw, uint8_t* out_nhwc, int32_t B, int32_t C, int32_t HW,
+                                    const double* mean, const double* stdv, pddm_stream_t s) {
+  if (!x_nchw || !out_nhwc || B <= 0 || C <= 0 || HW <= 0 || ((mean == nullptr) != (stdv == nullptr)))
+    return PDDM_ERR_BAD_ARG;
+  PdlLaunch(grid_for(static_cast<long long>(B) * C * HW, 256), 256, 0, S(s))(images_to_uint8_kernel, x_nchw, out_nhwc, B,
+                                                                           C, HW, mean, stdv);
+  return launch_status();
+}
 extern "C" int pddm_nhwc_slice_to_nchw(const float* src, float* dst, int32_t B, int32_t C, int32_t HW, int32_t ld,
                                        pddm_stream_t s) {
   if (!src || !dst || B <= 0 || C <= 0 || HW <= 0 || ld < C) return PDDM_ERR_BAD_ARG;

@@ -63,6 +63,11 @@ except Exception:  # pragma: no cover - depends on the environment
 LN2 = float(np.log(2.0))
 
 
+# src/datasets/data.py:24-28
+NORMALIZATIONS = {"cifar": ((0.485, 0.456, 0.406), (0.229, 0.224, 0.225)), "mnist": ((0.5,), (0.5,)),
+                  "oneone": ((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))}
+
+
 class Engine(_Base):
     def __init__(self, model_config, optimizer_config, diffusion_steps=1000, beta_start=None, beta_end=None,
                  mode="linear", max_beta=0.999, sigma_mode="beta", resolution=32, clip_while_generating=False,
@@ -409,17 +414,39 @@ class Engine(_Base):
                             ("test_nll", "nll"), ("test_mse", "MSE")):
             self.log(k_out, nll[k_in])
 
-    def calculate_likelihood(self, x, t_batch=1):
+    def calculate_likelihood(self, x, t_batch=1, shard=None, group=None):
         """Eq. (5) of DDPM in bits/dim (src/engine.py:417-435).  ``t_batch`` > 1 (extension) evaluates that
         many timesteps per UNet forward by folding t into the batch dimension (the T-1 terms are independent); the
-        default reproduces the reference's one-forward-per-t loop and its noise draw order."""
-        L_0 = self._calculate_L_0(x)
-        L_intermediate_list, MSE_list = self._calculate_L_intermediate(x, t_batch)
-        L_T = self._calculate_L_T(x)
-        L_intermediate = torch.sum(torch.stack(L_intermediate_list), dim=0)
-        return {"MSE": torch.mean(torch.stack(MSE_list)), "MSE_list": MSE_list, "L_0": torch.mean(L_0, dim=0),
-                "L_intermediate": L_intermediate, "L_T": torch.mean(L_T, dim=0),
-                "nll": torch.mean(L_0 + L_intermediate + L_T, dim=0), "L_intermediate_list": L_intermediate_list}
+        default reproduces the reference's one-forward-per-t loop and its noise draw order.
+
+        ``shard=(rank, world)`` (extension): the T-1 intermediate terms are dealt round-robin to the
+        ranks (``parallel.shard_timesteps``), rank 0 adds L_0 and L_T, and ONE all-reduce of a [3B + 2] vector hands
+        every rank the complete result -- the only collective of the evaluation.  ``x`` is the same batch on every
+        rank (shard the batch with ``parallel.shard_batch`` first to split both ways)."""
+        if shard is None:
+            L_0 = self._calculate_L_0(x)
+            L_intermediate_list, MSE_list = self._calculate_L_intermediate(x, t_batch)
+            L_T = self._calculate_L_T(x)
+            L_intermediate = torch.sum(torch.stack(L_intermediate_list), dim=0)
+            return {"MSE": torch.mean(torch.stack(MSE_list)), "MSE_list": MSE_list, "L_0": torch.mean(L_0, dim=0),
+                    "L_intermediate": L_intermediate, "L_T": torch.mean(L_T, dim=0),
+                    "nll": torch.mean(L_0 + L_intermediate + L_T, dim=0), "L_intermediate_list": L_intermediate_list}
+        from . import parallel
+        rank, world = shard
+        steps = parallel.shard_timesteps(self.diffusion_steps, rank, world)
+        L_list, MSE_list = self._calculate_L_intermediate(x, t_batch, steps=steps)
+        B = x.shape[0]
+        zero = torch.zeros(B, dtype=torch.float32, device=self.device)
+        parts = {"L_int": torch.sum(torch.stack(L_list), dim=0) if L_list else zero,
+                 "L_0": self._calculate_L_0(x) if rank == 0 else zero,
+                 "L_T": self._calculate_L_T(x) if rank == 0 else zero,
+                 "mse_sum": sum((m.double().sum() for m in MSE_list), torch.zeros((), dtype=torch.float64,
+                                                                                 device=self.device)),
+                 "mse_count": float(sum(m.numel() for m in MSE_list))}
+        tot = parallel.all_reduce_nll(parts, group=group)
+        return {"MSE": (tot["mse_sum"] / max(tot["mse_count"], 1.0)).float(), "MSE_list": MSE_list,
+                "L_0": torch.mean(tot["L_0"], dim=0), "L_intermediate": tot["L_int"], "L_T": torch.mean(tot["L_T"], dim=0),
+                "nll": torch.mean(tot["L_0"] + tot["L_int"] + tot["L_T"], dim=0), "L_intermediate_list": L_list}
 
     def _vlb(self, x0, x_t, model_out, t, mode):
         out, _ = F.vlb_terms(x0.float().contiguous(), None if x_t is None else x_t.contiguous(),
@@ -431,13 +458,14 @@ class Engine(_Base):
         """KL(q(x_T|x_0) || N(0, I)) (src/engine.py:437-444)"""
         return self._vlb(x, None, None, None, 2)
 
-    def _calculate_L_intermediate(self, x0, t_batch=1) -> Tuple[List[torch.Tensor], List[torch.Tensor]]:
-        """sum_t KL(q(x_{t-1}|x_t,x_0) || p(x_{t-1}|x_t)), fixed variance (src/engine.py:446-475)"""
+    def _calculate_L_intermediate(self, x0, t_batch=1, steps=None) -> Tuple[List[torch.Tensor], List[torch.Tensor]]:
+        """sum_t KL(q(x_{t-1}|x_t,x_0) || p(x_{t-1}|x_t)), fixed variance (src/engine.py:446-475); ``steps``: the
+        subset of t in [2, T] this rank evaluates (default: all)."""
         L_list, MSE_list = [], []
         ones = torch.ones(x0.shape[0], dtype=torch.int64, device=self.device)
+        steps = list(range(2, self.diffusion_steps + 1)) if steps is None else list(steps)
         if t_batch > 1:
             B = x0.shape[0]
-            steps = list(range(2, self.diffusion_steps + 1))
             for i in range(0, len(steps), t_batch):
                 chunk = steps[i: i + t_batch]
                 t = torch.tensor(chunk, dtype=torch.int64, device=self.device).repeat_interleave(B)
@@ -451,7 +479,7 @@ class Engine(_Base):
                 L_list.extend(kl.unbind(0))
                 MSE_list.extend(mse.unbind(0))
             return L_list, MSE_list
-        for t_step in range(2, self.diffusion_steps + 1):
+        for t_step in steps:
             t = ones * t_step
             noise = torch.randn_like(x0)
             x_t = self.get_q_t(x0, noise, t)
@@ -499,6 +527,27 @@ class Engine(_Base):
                               generator=generator, device=self.device)
             x_t = self.sample_from_step(x_t, self.diffusion_steps, mean_only=mean_only, generator=generator)
             images.append(x_t.detach().cpu().numpy())
+        return np.concatenate(images, axis=0)
+
+    @torch.no_grad()
+    def generate_images_uint8(self, n=1, minibatch=4, mean_only=False, seed=None, normalize=None):
+        """``generate_images`` followed by the reference's host post-processing (src/modules/fid_score.py:15-27:
+        ``unnormalize(img, normalize, clip=True)`` per image, then the writer's ``(255 * A).astype(uint8)``) done on
+        the device: each mini-batch is clamped, un-normalised and quantised by one kernel and leaves as ONE uint8 NHWC
+        copy (a quarter of the fp32 bytes).  Same RNG stream as ``generate_images``.  ``normalize``: None (the
+        reference's call), a (mean, std) pair, or a key of NORMALIZATIONS (src/datasets/data.py:24-28).
+        Returns uint8 [N, H, W, C]."""
+        self.eval()
+        mean = std = None
+        if normalize is not None:
+            mean, std = NORMALIZATIONS[normalize] if isinstance(normalize, str) else normalize
+        generator = get_generator_if_specified(seed, device=self.device)
+        images = []
+        for _ in range(int(np.ceil(n / minibatch))):
+            x_t = torch.randn((minibatch, self.model.in_channels, self.resolution, self.resolution),
+                              generator=generator, device=self.device)
+            x_t = self.sample_from_step(x_t, self.diffusion_steps, mean_only=mean_only, generator=generator)
+            images.append(F.images_to_uint8(x_t.float().contiguous(), mean, std).cpu().numpy())
         return np.concatenate(images, axis=0)
 
     @torch.no_grad()

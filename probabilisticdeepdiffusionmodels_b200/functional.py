@@ -644,6 +644,22 @@ def vlb_terms(x0, x_t, model_out, t, tabs: DeviceTables, mode, sigma_mode="beta"
     return out, gv
 
 
+def images_to_uint8(x, mean=None, std=None):
+    """fp32 NCHW samples -> uint8 NHWC pixels: uint8(255 * clip(x * std + mean, 0, 1)) in one pass (the reference's
+    unnormalize(clip=True) + image writer, src/datasets/data.py:108-128).  mean/std: per-channel sequences or None."""
+    L.require_device(x)
+    _chk(x, f32)
+    B, Cc = x.shape[0], x.shape[1]
+    out = torch.empty((B,) + tuple(x.shape[2:]) + (Cc,), dtype=torch.uint8, device=x.device)
+    m = s = None
+    if mean is not None:
+        m = torch.tensor(list(mean), dtype=torch.float64, device=x.device)
+        s = torch.tensor(list(std), dtype=torch.float64, device=x.device)
+        assert m.numel() == Cc and s.numel() == Cc
+    L.call("pddm_images_to_uint8", L.ptr(x), L.ptr(out), B, Cc, x.numel() // (B * Cc), L.ptr(m), L.ptr(s), L.stream())
+    return out
+
+
 def step_advance(t_dev, t_vec):
     L.call("pddm_step_advance", L.ptr(t_dev), L.ptr(t_vec), t_vec.shape[0], L.stream())
 

@@ -37,6 +37,26 @@ def shard_batch(x, rank, world):
     return x[lo: lo + base + (1 if rank < rem else 0)]
 
 
+def shard_timesteps(diffusion_steps, rank, world):
+    """The intermediate NLL terms t = 2 ... T (src/engine.py:455) dealt round-robin to ``world`` ranks: rank r takes
+    t = 2 + r, 2 + r + world, ...  (every t exactly once; consecutive ranks see similar noise levels, i.e. similar work)."""
+    return list(range(2 + rank, diffusion_steps + 1, world))
+
+
+def all_reduce_nll(parts, group=None):
+    """Sum the ranks' partial NLL results with ONE all-reduce: ``parts`` = {"L_int", "L_0", "L_T": fp32 [B] per-sample
+    vectors, "mse_sum": 0-dim float64 tensor, "mse_count": float}.  Returns the totals (same keys) on every rank."""
+    B = parts["L_int"].shape[0]
+    dev = parts["L_int"].device
+    flat = torch.cat([parts["L_int"].double(), parts["L_0"].double(), parts["L_T"].double(),
+                      parts["mse_sum"].double().reshape(1),
+                      torch.tensor([parts["mse_count"]], dtype=torch.float64, device=dev)])
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return {"L_int": flat[:B].float(), "L_0": flat[B: 2 * B].float(), "L_T": flat[2 * B: 3 * B].float(),
+            "mse_sum": flat[3 * B], "mse_count": float(flat[3 * B + 1])}
+
+
 class FlatGradAllReduce:
     """``hook(params)``: average ``p.grad`` over the process group through one flat bucket.
 

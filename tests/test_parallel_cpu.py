@@ -146,3 +146,40 @@ def test_arena_grad_allreduce(tmp_path):
     out = str(tmp_path / "res.pt")
     mp.spawn(_worker_arena, args=(2, _free_port(), out), nprocs=2, join=True)
     assert torch.load(out)["ok"]
+
+
+def test_shard_timesteps_covers_every_term_once():
+    from probabilisticdeepdiffusionmodels_b200.parallel import shard_timesteps
+    for T in (2, 3, 20, 1000):
+        for world in (1, 2, 3, 8):
+            got = sorted(t for r in range(world) for t in shard_timesteps(T, r, world))
+            assert got == list(range(2, T + 1))
+
+
+def _worker_nll(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from probabilisticdeepdiffusionmodels_b200 import parallel
+    parallel.init_from_env("gloo")
+    T, B = 50, 4
+    f = lambda t: torch.arange(B, dtype=torch.float32) * 0.01 + 1.0 / t  # per-sample term of timestep t
+    mine = parallel.shard_timesteps(T, rank, world)
+    parts = {"L_int": sum((f(t) for t in mine), torch.zeros(B)),
+             "L_0": torch.full((B,), 3.0) if rank == 0 else torch.zeros(B),
+             "L_T": torch.full((B,), 0.5) if rank == 0 else torch.zeros(B),
+             "mse_sum": torch.tensor(float(sum(mine)), dtype=torch.float64), "mse_count": float(len(mine))}
+    tot = parallel.all_reduce_nll(parts)
+    want = sum((f(t) for t in range(2, T + 1)), torch.zeros(B))
+    assert torch.allclose(tot["L_int"], want, rtol=1e-6)
+    assert torch.equal(tot["L_0"], torch.full((B,), 3.0)) and torch.equal(tot["L_T"], torch.full((B,), 0.5))
+    assert float(tot["mse_sum"]) == float(sum(range(2, T + 1))) and tot["mse_count"] == float(T - 1)
+    if rank == 0:
+        torch.save({"ok": True}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_nll_reduction(tmp_path):
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_worker_nll, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert torch.load(out)["ok"]
