@@ -423,6 +423,19 @@ int64_t pddm_attn_bwd_workspace_bytes(int32_t B, int32_t T, int32_t heads, int32
 int pddm_attn_bwd(const pddm_attn_bwd_params* p, pddm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------
+ * Opt-in high-precision forward (highprec.py): fp32 activations, every GEMM operand split into bf16 hi + lo terms
+ * (x = hi + lo, hi = bf16(x), lo = bf16(x - hi)) so that W x = W_hi x_hi + W_hi x_lo + W_lo x_hi runs on the bf16
+ * tap-GEMM with fp32 accumulation.  pddm_split_bf16: n elements.  pddm_gn_split_f32: GroupNorm (+SiLU) of an fp32
+ * [B, HW, C] tensor, statistics written to mean / rstd [B, G], result written as the split pair (and, if y32 != NULL,
+ * as fp32).  pddm_attn_fwd_f32: QKVAttention (src/modules/unet.py:237-256) in plain fp32 on [B, T, 3*heads*d].
+ * ---------------------------------------------------------------------------------------------------- */
+int pddm_split_bf16(const float* x, void* hi, void* lo, int64_t n, pddm_stream_t stream);
+int pddm_gn_split_f32(const float* x, const float* gamma, const float* beta, float* mean, float* rstd, void* hi, void* lo,
+                      float* y32, int32_t B, int32_t HW, int32_t C, int32_t G, float eps, int32_t silu,
+                      pddm_stream_t stream);
+int pddm_attn_fwd_f32(const float* qkv, float* out, int32_t B, int32_t T, int32_t heads, int32_t d, pddm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
  * Fused Adam (+ EMA) over a flat fp32 parameter arena (torch.optim.Adam defaults, src/engine.py:238-248;
  * Ema.update src/modules/ema.py:21-33).  ema may be NULL.  step is the 1-based step count.
  * ---------------------------------------------------------------------------------------------------- */

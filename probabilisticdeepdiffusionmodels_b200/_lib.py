@@ -158,6 +158,10 @@ SIGNATURES = {
     "pddm_attn_fwd": (c_i32, [P(AttnFwdParams), c_vp]),
     "pddm_attn_bwd": (c_i32, [P(AttnBwdParams), c_vp]),
     "pddm_attn_bwd_workspace_bytes": (c_i64, [c_i32, c_i32, c_i32, c_i32]),
+    "pddm_split_bf16": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "pddm_gn_split_f32": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_i32,
+                                  c_vp]),
+    "pddm_attn_fwd_f32": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "pddm_adam_ema_step": (c_i32, [P(AdamParams), c_vp]),
     "pddm_adam_ema_multi": (c_i32, [c_vp, c_vp, c_i32, P(AdamParams), c_vp]),
     "pddm_counter_add": (c_i32, [c_vp, c_i32, c_vp]),

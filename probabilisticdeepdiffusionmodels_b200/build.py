@@ -14,7 +14,7 @@ CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(PKG, "libpddm_b200.so")
 SOURCES = ["host_common.cu", "conv_fwd.cu", "conv_wgrad.cu", "diffusion.cu", "layout.cu", "groupnorm.cu", "groupnorm_pipe.cu",
-           "attention.cu"]
+           "attention.cu", "highprec.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
 
