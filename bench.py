@@ -52,6 +52,13 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
+
+    def mark_start(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def __enter__(self):
         try:
@@ -66,7 +73,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def __exit__(self, *a):
         if self.proc is not None:
@@ -79,7 +86,15 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        # the sampler is started before the warm-up steps (nvidia-smi takes a second to come up, longer than the
+        # timed region itself): keep the samples taken inside the timed region; if the region was shorter than the
+        # sampling period, the samples of the (identical, back-to-back) warm-up steps right before it stand in
+        inside = [r for (ts, r) in self.rows if self.t0 is not None and self.t0 <= ts <= (self.t1 or ts)]
+        scope = "timed region"
+        if not inside:
+            inside = [r for (ts, r) in self.rows if self.t0 is None or ts <= (self.t1 or ts)][-10:]
+            scope = "warm-up steps immediately before the timed region"
+        for r in inside:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -90,7 +105,7 @@ class ClockSampler:
                 pass
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "scope": scope}
 
 
 def measured_traffic():
@@ -379,16 +394,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(max(args.warmup, 3)):
-        step(x_dev)
-    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
+        for _ in range(max(args.warmup, 3)):
+            step(x_dev)
+        if clk.proc is not None:  # keep the GPU under the same load until the sampler has produced its first rows
+            deadline = time.perf_counter() + 4.0
+            while not clk.rows and time.perf_counter() < deadline:
+                step(x_dev)
+        barrier()
+        clk.mark_start()
         e0.record()
         for _ in range(args.steps):
             eng._train_graph["graph"].replay()
         e1.record()
         barrier()
+        clk.mark_end()
     ms = e0.elapsed_time(e1) / args.steps
 
     # end-to-end through the public step(x): pinned host batch -> device each step, loss read back each step
