@@ -221,6 +221,50 @@ def cpu_reference_arm(steps, warmup, batch=None, threads=None):
                       f"sampling = {nst} reverse steps at B={batch} extrapolated x1000/{nst} to 1000-step chains"}
 
 
+def unmodified_reference_arm(steps, warmup, batch, threads=None):
+    """The reference's OWN Engine (staged under baseline/_ref by __graft_entry__.build(); git-ignored) timed on the
+    host cores: ``Engine.training_step`` + backward + torch Adam on the same architecture, schedule and batch.  The
+    reference hard-codes learn_sigma=False (src/modules/__init__.py:34), so this is L_simple with the 3-channel head --
+    what the reference actually trains; the oracle port (``cpu_reference_arm``) adds the learned-variance L_hybrid of
+    the measured arm.  Returns None when the staged copy is absent."""
+    root = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(root, "src")):
+        return None
+    import torch
+
+    os.environ["PDDM_REFERENCE_ROOT"] = root
+    from oracle import ref_shims
+    from oracle.unet_ref import MODEL_CONFIGS
+    ref_shims.REFERENCE_ROOT = root
+    ref_shims.install()
+    from src.engine import Engine  # the reference's, not this package's
+
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    with __import__("contextlib").redirect_stdout(sys.stderr):  # the reference prints its settings: keep stdout = one JSON line
+        eng = Engine(dict(MODEL_CONFIGS[MODEL]), {"lr": 1e-4}, diffusion_steps=1000, mode="cosine", resolution=RES)
+    opt = torch.optim.Adam(eng.parameters(), lr=1e-4)
+    x0 = torch.rand((batch, 3, RES, RES)) * 2 - 1
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = eng.training_step((x0, None), 0)
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return {"train_img_s": batch / dt, "ms_per_step": dt * 1e3, "cores": threads, "batch": batch,
+            "what": "unmodified reference Engine.training_step + backward + torch.optim.Adam (L_simple, fixed variance: "
+                    "the reference has no learned-variance path), fp32, CPU"}
+
+
 def micro_diffusion():
     """HBM evidence for the fused elementwise diffusion kernels (north_star group 4): time
     q_sample / p_sample / vlb / sq_err at the training batch (B=128: 1.5 MB tensors, launch-bound) and at a
@@ -333,6 +377,10 @@ def main():
         steps = max(1, min(args.steps, 3))
         warm = max(1, min(args.warmup, 1))
         r = cpu_reference_arm(steps, warm, batch=args.batch)
+        try:
+            unmod = unmodified_reference_arm(max(1, steps - 1), 1, args.batch)
+        except Exception as e:  # the staged copy is optional evidence; the port is the arm
+            unmod = {"error": str(e)[:200]}
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": r["train_img_s"], "unit": "img/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
@@ -341,6 +389,7 @@ def main():
                          "image_steps_per_s": r["image_steps_s"]},
             "cpu_baseline": {"value": r["train_img_s"], "unit": "img/s", "cores": r["cores"], "kind": "port",
                              "sample": r["sample"]},
+            "unmodified_reference": unmod,
             "e2e": {"value": r["train_img_s"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
