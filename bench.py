@@ -334,6 +334,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--bucketed-allreduce", action="store_true",
                     help="N>1: all-reduce bucket by bucket from inside backward on a communication stream")
+    ap.add_argument("--allreduce", default="overlap", choices=["overlap", "flat"],
+                    help="N > 1: arena all-reduce hidden under the backward pass (default) or one call after it")
+    ap.add_argument("--overlap-comm", default="own", choices=["own", "own-default", "same"],
+                    help="communicator of the overlapped ranges: own (max_ctas = sm reserve), own-default, same")
+    ap.add_argument("--sm-reserve", type=int, default=8,
+                    help="SMs left to NCCL while an overlapped all-reduce is in flight (= its max_ctas)")
     ap.add_argument("--config", default="cifar", choices=sorted(CONFIGS),
                     help="cifar = BASELINE configs[1] (the metric's configuration); celeba64 = configs[4]")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
@@ -346,6 +352,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="keep weight-gradient GEMMs on the main stream")
     args = ap.parse_args()
+    if os.environ.get("PDDM_BENCH_WATCHDOG"):  # debugging aid: dump every thread's Python stack and exit if we hang
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["PDDM_BENCH_WATCHDOG"]), exit=True)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     global METRIC, MODEL, RES, PER_GPU_BATCH
@@ -428,9 +437,13 @@ def main():
         if args.bucketed_allreduce:
             hook = parallel.BucketedGradAllReduce(eng.model.parameters())
         elif _plan.plan_for(eng.model, x_dev) is not None:
-            # gradients live in one flat arena: all-reduce it in place, fold 1/W into the Adam kernel
+            # gradients live in one flat arena: all-reduce it in place, fold 1/W into the Adam kernel; by default the
+            # tail ranges of the arena are reduced under the backward pass (--allreduce flat: one call after it)
             optimizer = FusedAdam(eng.model.parameters(), lr=1e-4)
-            hook = parallel.ArenaGradAllReduce(optimizer)
+            if args.allreduce == "overlap":
+                hook = parallel.OverlappedArenaAllReduce(optimizer, sm_reserve=args.sm_reserve, comm=args.overlap_comm)
+            else:
+                hook = parallel.ArenaGradAllReduce(optimizer)
         else:
             hook = parallel.FlatGradAllReduce()
 
@@ -447,10 +460,18 @@ def main():
     with ClockSampler(local_rank) as clk:
         for _ in range(max(args.warmup, 3)):
             step(x_dev)
-        if clk.proc is not None:  # keep the GPU under the same load until the sampler has produced its first rows
-            deadline = time.perf_counter() + 4.0
-            while not clk.rows and time.perf_counter() < deadline:
-                step(x_dev)
+        # keep the GPU under the same load until the sampler has produced its first rows -- on EVERY rank, and every
+        # rank leaves the loop after the same number of steps (a step contains collectives: ranks that replayed the
+        # graph a different number of times would pair mismatched all-reduces)
+        deadline = time.perf_counter() + 4.0
+        while True:
+            ready = torch.tensor([1 if (clk.proc is None or clk.rows or time.perf_counter() >= deadline) else 0],
+                                 dtype=torch.int32, device=dev)
+            if world > 1:
+                dist.all_reduce(ready, op=dist.ReduceOp.MIN)
+            if int(ready.item()):
+                break
+            step(x_dev)
         barrier()
         clk.mark_start()
         e0.record()

@@ -44,6 +44,13 @@ const char* pddm_strerror(int status);
 /* 0 if the current device can run the library (compute capability 10.x), PDDM_ERR_ARCH otherwise. */
 int pddm_check_device(void);
 int pddm_sm_count(void);
+/* Leave n SMs free in every subsequent launch of the persistent kernels (tap-GEMMs, weight gradients, pipelined
+ * GroupNorm size their grids to the SM count): room for a collective (NCCL) running concurrently on another stream,
+ * whose CTAs would otherwise have to wait for a GEMM CTA to finish -- or make the GEMM's last CTAs wait for them.
+ * Process-wide launch configuration (0 = whole device, the default); it never changes results beyond the summation
+ * order of split-K weight gradients.  Grids captured into a CUDA graph keep the value they were captured with. */
+int pddm_set_sm_reserve(int32_t n);
+int pddm_get_sm_reserve(void);
 
 /* ------------------------------------------------------------------------------------------------------
  * Diffusion math (fp32, NCHW, HBM-bound elementwise kernels)

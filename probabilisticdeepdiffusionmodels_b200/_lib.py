@@ -115,6 +115,8 @@ SIGNATURES = {
     "pddm_strerror": (C.c_char_p, [c_i32]),
     "pddm_check_device": (c_i32, []),
     "pddm_sm_count": (c_i32, []),
+    "pddm_set_sm_reserve": (c_i32, [c_i32]),
+    "pddm_get_sm_reserve": (c_i32, []),
     "pddm_q_sample": (c_i32, [P(QSampleParams), c_vp]),
     "pddm_sq_err": (c_i32, [P(SqErrParams), c_vp]),
     "pddm_p_sample_step": (c_i32, [P(PSampleParams), c_vp]),

@@ -817,7 +817,7 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
         (!p->residual || p->res_dtype == PDDM_BF16) && p->out_sh == 1 && p->out_sw == 1 && p->out_oh == 0 &&
         p->out_ow == 0 && p->out_H == p->H && p->out_W == p->W && pow2w && PW * PH * PB == 256 &&
         (PW * PH) % 32 == 0 &&
-        ((tiles >= 2 * device_info().sm_count && p->ntaps * (p->Cin / 64) >= 16) || env_knobs().conv_swap_force)) {
+        ((tiles >= 2 * launch_sms() && p->ntaps * (p->Cin / 64) >= 16) || env_knobs().conv_swap_force)) {
       a.swap = 1;
       a.BW = PW; a.BH = PH; a.BB = PB;
       a.tiles_w = (p->W + PW - 1) / PW;
@@ -868,7 +868,7 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
         if (rc) return rc;
       }
       if (ensure_smem_optin(reinterpret_cast<const void*>(conv_fwd_swap_kernel))) return PDDM_ERR_CUDA;
-      const int grid = tiles < device_info().sm_count ? tiles : device_info().sm_count;
+      const int grid = tiles < launch_sms() ? tiles : launch_sms();
       PdlLaunch(grid, kSwapThreads, smem_bytes, stream)(conv_fwd_swap_kernel, tmA, tmB, a);
       return launch_status();
     }
@@ -885,7 +885,7 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
   a.block_n = pick_block_n(p->Cout);
   // small spatial extents: trade B-operand reuse for enough tiles to occupy every SM
   while (a.block_n % 64 == 0 &&
-         a.m_tiles * ((p->Cout + a.block_n / 2 - 1) / (a.block_n / 2)) <= device_info().sm_count)
+         a.m_tiles * ((p->Cout + a.block_n / 2 - 1) / (a.block_n / 2)) <= launch_sms())
     a.block_n /= 2;
   a.n_tiles = (p->Cout + a.block_n - 1) / a.block_n;
   a.bk = (p->Cin % 64 == 0) ? 64 : 32;
@@ -977,7 +977,7 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
   }
   if (ensure_smem_optin(reinterpret_cast<const void*>(conv_fwd_kernel))) return PDDM_ERR_CUDA;
   const int total_tiles = ((a.m_tiles + a.mt - 1) / a.mt) * a.n_tiles;
-  const int grid = total_tiles < device_info().sm_count ? total_tiles : device_info().sm_count;
+  const int grid = total_tiles < launch_sms() ? total_tiles : launch_sms();
   PdlLaunch(grid, kConvThreads, smem_bytes, stream)(conv_fwd_kernel, tmA, tmA2, tmB, tmY, tmR, a);
   return launch_status();
 }

@@ -293,7 +293,7 @@ static int plan_wgrad(const pddm_wgrad_params* p, WgradPlan* plan) {
     a.tap_dw[i] = i < p->ntaps ? p->tap_dw[i] : 0;
   }
   const int base_items = a.ntaps * a.m_tiles * a.n_tiles;
-  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  const int sms = launch_sms();
   int splits = sms / base_items;  // one wave of work items: every extra split costs a full fp32 partial tile
   const int max_splits = (a.k_blocks + 7) / 8;           // but keep >= 8 K-blocks per split
   if (splits > max_splits) splits = max_splits;

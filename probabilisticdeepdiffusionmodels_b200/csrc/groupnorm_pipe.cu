@@ -655,7 +655,7 @@ static int make_map3(CUtensorMap* m, const void* base, int Cseg, int HW, int B, 
 }
 
 static int pipe_grid(const PipeGeom& g) {
-  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  const int sms = launch_sms();
   return g.nitems < sms ? g.nitems : sms;
 }
 

@@ -1,6 +1,7 @@
 #include <stdlib.h>
 #include "host_common.h"
 
+#include <atomic>
 #include <mutex>
 
 namespace pddm {
@@ -59,6 +60,13 @@ const DeviceInfo& device_info() {
     have[dev] = true;
   }
   return info[dev];
+}
+
+static std::atomic<int> g_sm_reserve{0};
+int launch_sms() {
+  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  const int r = g_sm_reserve.load();
+  return sms - r > 0 ? sms - r : sms;
 }
 
 int ensure_smem_optin(const void* fn) {
@@ -140,5 +148,12 @@ const char* pddm_strerror(int status) {
 
 int pddm_check_device(void) { return pddm::device_info().ok ? PDDM_OK : PDDM_ERR_ARCH; }
 int pddm_sm_count(void) { return pddm::device_info().sm_count; }
+int pddm_set_sm_reserve(int32_t n) {
+  const int sms = pddm::device_info().sm_count;
+  if (n < 0 || (sms > 0 && n > sms / 2)) return PDDM_ERR_BAD_ARG;
+  pddm::g_sm_reserve.store(n);
+  return PDDM_OK;
+}
+int pddm_get_sm_reserve(void) { return pddm::g_sm_reserve.load(); }
 
 }  // extern "C"

@@ -16,6 +16,10 @@ struct DeviceInfo {
   int max_smem_optin;
 };
 const DeviceInfo& device_info();
+// SMs the persistent kernels (one CTA per SM: tap-GEMMs, weight gradients, pipelined GroupNorm) size their grids for:
+// the device's SM count minus the reserve set through pddm_set_sm_reserve (SMs left to a concurrently running
+// collective, see include/pddm.h).  A launch-configuration knob: results never depend on it beyond summation order.
+int launch_sms();
 
 // Experiment knobs (environment variables), read ONCE per process -- the launch paths themselves are stateless
 // and never call getenv.  -1 = not set.

@@ -652,6 +652,10 @@ class Engine(_Base):
         from . import _lib, plan as _plan
         plan = _plan.plan_for(self.model, st["x"]) if all(p.requires_grad for p in self.model.parameters()) else None
         st["plan"] = plan
+        if plan is not None:
+            plan.comm = None
+            if grad_hook is not None and hasattr(grad_hook, "attach"):
+                grad_hook.attach(plan)  # overlapped all-reduce: the backward pass reports finished arena ranges
         B = batch_shape[0]
 
         def draw():

@@ -126,6 +126,11 @@ def tap_gemm(x, wp, taps, B, H, W, *, bias=None, bcast=None, residual=None, out=
     return out
 
 
+def set_sm_reserve(n):
+    """Leave ``n`` SMs free in subsequent launches of the persistent kernels (room for a concurrent collective)."""
+    L.check(L.load().pddm_set_sm_reserve(int(n)), "pddm_set_sm_reserve")
+
+
 def wgrad_workspace_bytes(B, H, W, cin, cout, ntaps, x_NB=None):
     """Bytes of split-K workspace ``tap_wgrad`` needs for this shape (host-side query, no launch)."""
     p = L.WgradParams()

@@ -114,6 +114,96 @@ class ArenaGradAllReduce:
             flat.mul_(1.0 / dist.get_world_size(self.group))
 
 
+class OverlappedArenaAllReduce:
+    """The arena all-reduce hidden under the backward pass of the hand-scheduled step (plan.py).
+
+    The gradient arena is laid out in the order the backward pass finishes its parts, last first
+    (``plan.bucket_bounds``): [small parameters, emb_layers, time_embed, stem, full-resolution encoder | encoder below
+    full resolution | middle block, decoder, head].  ``plan.backward`` calls ``range_final`` as soon as every kernel
+    that writes a tail range has been issued; the range is all-reduced on a high-priority communication stream (after
+    the main and the weight-gradient streams' work issued so far) while the backward pass goes on.  ``hook(plan)``
+    after the backward pass reduces the head of the arena -- all that is still exposed, ~14 % of the bytes for the
+    CIFAR UNet -- and joins the streams.  1/W is folded into the fused Adam kernel (``optimizer.grad_scale``).
+
+    Why the SM reserve: the GEMM kernels are persistent, one CTA per SM, each with a fixed share of the tiles.  NCCL's
+    CTAs cannot share an SM with them (shared memory), so either NCCL waits for a whole GEMM kernel or -- once it holds
+    its SMs -- the GEMM's CTAs that found no SM run as a second wave and double that kernel's time (what r1 measured
+    as "bucketing is neutral").  While a range is in flight the persistent kernels are therefore launched on
+    ``sm_count - sm_reserve`` SMs (``pddm_set_sm_reserve``) and the communicator of the overlapped ranges is created
+    with ``max_ctas = sm_reserve``.  The head of the arena goes through the default group (all CTAs NCCL wants: it is
+    exposed anyway).  Works inside CUDA-graph capture (fork / join become graph edges) and on CPU tensors with gloo
+    (no streams, no reserve)."""
+
+    takes_plan = True
+
+    def __init__(self, optimizer=None, group=None, sm_reserve=8, overlap_group=None, comm="own"):
+        self.group, self.sm_reserve = group, int(sm_reserve)
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if optimizer is not None:
+            optimizer.grad_scale = 1.0 / world
+        self.scale_in_optimizer = optimizer is not None
+        self.overlap_group = overlap_group
+        # comm: "own" = a communicator of its own limited to sm_reserve CTAs; "own-default" = of its own, NCCL's
+        # defaults; "same" = the group's communicator
+        if overlap_group is None and comm != "same" and dist.is_initialized() and world > 1 and \
+                dist.get_backend(group) == "nccl":
+            opts = dist.ProcessGroupNCCL.Options()
+            if comm == "own":
+                opts.config.max_ctas = max(1, self.sm_reserve)
+                opts.config.min_ctas = 1
+            ranks = dist.get_process_group_ranks(group) if group is not None else list(range(world))
+            self.overlap_group = dist.new_group(ranks=ranks, backend="nccl", pg_options=opts)
+        self.stream = None
+        self._done_from = None  # arena offset from which everything has been handed to the communication stream
+
+    def _active(self):
+        return dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def attach(self, plan):
+        """Have ``plan.backward`` report finished arena ranges to this object."""
+        plan.comm = self if self._active() else None
+        return self
+
+    def range_final(self, plan, lo, hi):
+        """Every kernel writing ``plan.grad_arena[lo:hi]`` has been issued (main or weight-gradient stream)."""
+        if not self._active() or hi <= lo:
+            return
+        flat = plan.grad_arena
+        if self._done_from is not None and hi != self._done_from:
+            raise RuntimeError("OverlappedArenaAllReduce: ranges must arrive tail first and be contiguous")
+        if flat.is_cuda:
+            from . import functional as F
+            dev = flat.device
+            if self.stream is None:
+                self.stream = torch.cuda.Stream(device=dev, priority=-1)
+            self.stream.wait_stream(torch.cuda.current_stream(dev))
+            if getattr(plan, "side", None) is not None and getattr(plan, "overlap", False):
+                self.stream.wait_stream(plan.side)
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=self.overlap_group or self.group)
+            if self.sm_reserve > 0:
+                F.set_sm_reserve(self.sm_reserve)  # kernels launched from here on leave NCCL its SMs
+        else:
+            dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+        self._done_from = lo
+
+    def __call__(self, plan):
+        if not self._active():
+            return
+        flat = plan.grad_arena
+        head = flat.numel() if self._done_from is None else self._done_from
+        self._done_from = None
+        if flat.is_cuda:
+            from . import functional as F
+            F.set_sm_reserve(0)
+            if self.stream is not None:  # join first: two communicators are never in flight together
+                torch.cuda.current_stream(flat.device).wait_stream(self.stream)
+        if head > 0:
+            dist.all_reduce(flat[:head], op=dist.ReduceOp.SUM, group=self.group)
+        if not self.scale_in_optimizer:
+            flat.mul_(1.0 / dist.get_world_size(self.group))
+
+
 class BucketedGradAllReduce:
     """Gradient averaging that overlaps the backward pass: ``hook = BucketedGradAllReduce(params)`` registers a
     post-accumulate-grad hook on every parameter; as soon as the gradients of one bucket (parameters in the order

@@ -90,6 +90,8 @@ class UNetPlan:
         self._keep = []
         self.wg_bytes = 16       # split-K workspace of the conv weight gradients (side stream)
         self.wg_bytes_main = 16  # ... of the few weight gradients issued on the main stream (stem, head, embedding)
+        self.comm = None         # parallel.OverlappedArenaAllReduce: told when a range of the gradient arena is final
+        self._gi_down = self._gi_mid = None  # index in self.gemms of the first weight of the first Downsample / middle block
 
         # ---- timestep embedding MLP and the batched emb_layers projection
         self.te0 = self._gemm(model.time_embed[0].weight, model.time_embed[0].bias, 1, need_dgrad=False)
@@ -124,6 +126,8 @@ class UNetPlan:
                 elif isinstance(layer, AttentionBlock):
                     nodes.append(_AttnNode(self, layer, H, W))
                 elif isinstance(layer, Downsample):
+                    if self._gi_down is None:
+                        self._gi_down, self._enc_down = len(self.gemms), len(enc_nodes)
                     nodes.append(_DownNode(self, layer, H, W))
                     H, W = H // 2, W // 2
                 else:
@@ -132,6 +136,7 @@ class UNetPlan:
             chans.append(ch)
         self.enc = enc_nodes
         self.mid = []
+        self._gi_mid = len(self.gemms)
         for layer in model.middle_block:
             self.mid.append(_ResNode(self, layer, ch, 0, H, W) if isinstance(layer, ResBlock)
                             else _AttnNode(self, layer, H, W))
@@ -194,7 +199,11 @@ class UNetPlan:
 
     def _build_arenas(self):
         dev = self.dev
-        # ---------------- gradient arena: [emb_layers weights, block order | other weights | folded small | direct small]
+        # ---------------- gradient arena, in the order the backward pass FINISHES its parts, last first:
+        #   [folded small | direct small | emb_layers weights | time_embed, stem, full-resolution encoder |
+        #    encoder from the first Downsample on | middle block, decoder, head]
+        # so that a data-parallel run can all-reduce the tail ranges while the backward pass is still producing the
+        # head of the arena (``bucket_bounds``; parallel.OverlappedArenaAllReduce)
         emb_w = [m.emb_layers[1].weight for m in self.res_blocks]
         emb_ids = {id(w) for w in emb_w}
         big = emb_w + [g.w for g in self.gemms if id(g.w) not in emb_ids]
@@ -204,9 +213,6 @@ class UNetPlan:
                 seen.add(id(w))
                 order.append(w)
         off, self.goff = 0, {}
-        for w in order:
-            self.goff[id(w)] = off
-            off += (w.numel() + 3) // 4 * 4
         self.small_off = off
         src_of = []
         for prm, col0 in self.small:
@@ -218,11 +224,25 @@ class UNetPlan:
         for prm in self.direct_small:
             self.goff[id(prm)] = off
             off += (prm.numel() + 3) // 4 * 4
+        off = (off + 1023) // 1024 * 1024
+        for w in order:
+            self.goff[id(w)] = off
+            off += (w.numel() + 3) // 4 * 4
         covered = set(self.goff)
         missing = [n for n, p_ in self.model.named_parameters() if id(p_) not in covered]
         if missing:
             raise ValueError(f"UNetPlan: parameters without a gradient slot: {missing[:4]}")
         self.grad_arena = torch.zeros(off, dtype=f32, device=dev)
+
+        def first_weight_off(gi):
+            ws = [g.w for g in self.gemms[gi:] if id(g.w) not in emb_ids]
+            return self.goff[id(ws[0])] if ws else off
+
+        b_mid = first_weight_off(self._gi_mid)
+        b_down = first_weight_off(self._gi_down) if self._gi_down is not None else b_mid
+        # [0, b_down): final at the very end; [b_down, b_mid): once the first Downsample's backward has been issued;
+        # [b_mid, end): once the middle block's backward has been issued
+        self.bucket_bounds = (b_down, b_mid, off)
         self.src_of = torch.tensor(src_of, dtype=torch.int32, device=dev)
         self.params = list(self.model.parameters())
         for g in self.gemms:
@@ -459,6 +479,9 @@ class UNetPlan:
             g = nd.bwd(g, S, self.sink(nd))
         last = n_enc - 1
         self.mid[0].bwd(g, S, Sink(self.cs_view(self.enc[last][-1].out_cs, self.enc[last][-1].cout), skip_g[last], True))
+        b_down, b_mid, b_end = self.bucket_bounds
+        if self.comm is not None:  # every gradient of the middle block, the decoder and the head has been issued
+            self.comm.range_final(self, b_mid, b_end)
         for i in reversed(range(1, n_enc)):
             g = skip_g.pop(i)
             nodes = self.enc[i]
@@ -466,6 +489,8 @@ class UNetPlan:
                 g = nd.bwd(g, S, self.sink(nd))
             prev = self.enc[i - 1][-1]
             nodes[0].bwd(g, S, Sink(self.cs_view(prev.out_cs, prev.cout), skip_g[i - 1], True))
+            if self.comm is not None and self._gi_down is not None and i == self._enc_down and b_down < b_mid:
+                self.comm.range_final(self, b_down, b_mid)  # ... and of the encoder below full resolution
         self.stem.bwd(skip_g.pop(0), S)
         self._emb_backward(S)
         F.batch_fold(self.ps, self.src_of, self.n_fold, self.grad_arena[self.small_off:])

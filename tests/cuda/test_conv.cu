@@ -281,6 +281,10 @@ int main(int argc, char** argv) {
     add1("1x1 slice ld512 off256", 2, 8, 8, 256, 512, 256, 128, PDDM_F32);
     add1("linear 200x512->1000", 1, 1, 200, 512, 512, 0, 1000, PDDM_F32);
     add1("qkv 1x1 16x16 256->768 b2", 2, 16, 16, 256, 256, 0, 768, PDDM_BF16);
+    // many tiles per CTA, odd tile counts, several channel tiles
+    add3("3x3 16x16 64->768 b25", 25, 16, 16, 64, 768, 1, 1, PDDM_BF16, PDDM_BF16);
+    add1("1x1 8x8 128->2048 b37", 37, 8, 8, 128, 128, 0, 2048, PDDM_BF16);
+    add3("3x3 8x8 96->640 b60", 60, 8, 8, 96, 640, 1, 0, -1, PDDM_BF16);
     {  // stride-2 as taps over a phase-split tensor [4B, H/2, W/2, C] + strided output mapping
       Case c; memset(&c, 0, sizeof(c));
       c.name = "phase taps + out stride"; c.B = 2; c.x_NB = 8; c.H = 8; c.W = 8; c.Cin = 64; c.ldx = 64; c.Cout = 64;
@@ -307,8 +311,11 @@ int main(int argc, char** argv) {
     add1("1x1 32x32 256->128 b128", 128, 32, 32, 256, 256, 0, 128, PDDM_BF16);
     add3("3x3 16x16 256->256 b128 +res", 128, 16, 16, 256, 256, 1, 1, PDDM_BF16, PDDM_BF16);
   }
+  // optional: `big <case index>` runs a single case (for ncu captures)
+  const int only = argc > 2 ? atoi(argv[2]) : -1;
   int fails = 0;
-  for (auto& c : cases) fails += run_case(c);
+  for (size_t i = 0; i < cases.size(); ++i)
+    if (only < 0 || static_cast<int>(i) == only) fails += run_case(cases[i]);
   printf("%s: %d failing checks\n", fails ? "FAILED" : "ALL OK", fails);
   return fails ? 1 : 0;
 }

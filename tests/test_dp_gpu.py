@@ -64,6 +64,73 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+def _worker_overlap(rank, world, port, out):
+    """Captured data-parallel training steps: all-reduce hidden under the backward pass (arena ranges reduced on a
+    communication stream as they become final, persistent kernels launched with an SM reserve) == the flat
+    all-reduce after the backward pass."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import faulthandler
+    faulthandler.dump_traceback_later(150, exit=True)  # a collective that never completes fails the test with a stack
+    from oracle.unet_ref import MODEL_CONFIGS, arch_from_config, make_params
+    from probabilisticdeepdiffusionmodels_b200 import Engine, parallel
+    from probabilisticdeepdiffusionmodels_b200 import _lib
+    from probabilisticdeepdiffusionmodels_b200.optim import FusedAdam
+    parallel.init_from_env("nccl")
+    dev = torch.device("cuda", rank)
+    torch.cuda.set_device(dev)
+    cfg = MODEL_CONFIGS["unet_small"]
+    arch = arch_from_config(32, **{k: v for k, v in cfg.items() if k != "name"})
+    B = 16
+    rs = np.random.RandomState(rank)
+    x0 = torch.from_numpy((rs.rand(B, 3, 32, 32) * 2 - 1).astype(np.float32)).to(dev)
+    finals = []
+    for mode in ("flat", "overlap"):
+        eng = Engine(dict(cfg), {"lr": 1e-3}, diffusion_steps=1000, mode="cosine", resolution=32,
+                     log_loss_per_t=False)
+        eng.model.load_state_dict(make_params(arch, seed=3))
+        eng = eng.to(dev)
+        opt = FusedAdam(eng.model.parameters(), lr=1e-3)
+        hook = parallel.ArenaGradAllReduce(opt) if mode == "flat" else parallel.OverlappedArenaAllReduce(opt, sm_reserve=8)
+        torch.manual_seed(100 + rank)  # the graph draws t and noise from the device generator
+        torch.cuda.manual_seed(100 + rank)
+        step = eng.capture_train_step((B, 3, 32, 32), optimizer=opt, grad_hook=hook)
+        assert step.state["plan"] is not None
+        if mode == "overlap":
+            assert step.state["plan"].comm is hook
+        losses = [float(step(x0)) for _ in range(3)]
+        torch.cuda.synchronize(dev)
+        assert _lib.load().pddm_get_sm_reserve() == 0  # the reserve is lifted at the end of every step
+        finals.append((losses, torch.cat([p.detach().flatten() for p in eng.model.parameters()]).clone()))
+    (l0, w0), (l1, w1) = finals
+    # capture runs 3 eager + 1 captured step before the 3 replays in both modes; t / noise streams may differ between
+    # the two engines, so compare the weights' agreement ACROSS RANKS (the point of the all-reduce) and finiteness
+    mine = w1.clone()
+    other = w1.clone()
+    dist.broadcast(other, src=0)
+    res = {"rank_diff": float((mine - other).abs().max()), "finite": bool(torch.isfinite(w1).all()),
+           "moved": float((w1 - w0).abs().max()), "losses": l1}
+    gathered = [None] * world
+    dist.all_gather_object(gathered, res)
+    if rank == 0:
+        torch.save(gathered, out)
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    # leave without NCCL's destructors: tearing down communicators that captured CUDA graphs still reference blocks
+    # in ncclCommDestroy (same exit path as bench.py)
+    os._exit(0)
+
+
+def test_overlapped_allreduce_keeps_ranks_identical(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_worker_overlap, args=(2, _free_port(), out), nprocs=2, join=True)
+    for r in torch.load(out):
+        print(f"[dp overlap] max |w_rank - w_rank0| = {r['rank_diff']:.3e}, losses {r['losses']}")
+        assert r["finite"] and r["rank_diff"] == 0.0  # every rank applied the same averaged gradient, bit for bit
+
+
 def test_two_gpu_step_equals_single_gpu_step_on_the_concatenated_batch(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")

@@ -136,6 +136,27 @@ def _worker_arena(rank, world, port, out):
     Plan.grad_arena = torch.ones(100) * (rank + 1)
     parallel.ArenaGradAllReduce(None)(Plan)  # no optimizer to carry the scale: averaged in place
     assert torch.allclose(Plan.grad_arena, torch.full((100,), 1.5))
+    # overlapped form: the backward pass reports finished tail ranges, the hook reduces the head and joins
+    opt2 = Opt()
+    hook = parallel.OverlappedArenaAllReduce(opt2)
+    want = torch.arange(5000, dtype=torch.float32) * sum(r + 1 for r in range(world))
+    for _ in range(2):  # reusable step after step
+        Plan.grad_arena = torch.arange(5000, dtype=torch.float32) * (rank + 1)
+        Plan.comm = None
+        hook.attach(Plan)
+        assert Plan.comm is hook
+        hook.range_final(Plan, 3000, 5000)
+        assert torch.equal(Plan.grad_arena[3000:], want[3000:]) and torch.equal(
+            Plan.grad_arena[:3000], torch.arange(3000, dtype=torch.float32) * (rank + 1))
+        hook.range_final(Plan, 1024, 3000)
+        hook(Plan)
+        assert opt2.grad_scale == 1.0 / world and torch.equal(Plan.grad_arena, want)
+    try:  # ranges must be contiguous, tail first
+        hook.range_final(Plan, 3000, 5000)
+        hook.range_final(Plan, 0, 1000)
+        raise AssertionError("non-contiguous range accepted")
+    except RuntimeError:
+        hook._done_from = None
     if rank == 0:
         torch.save({"ok": True}, out)
     dist.barrier()
