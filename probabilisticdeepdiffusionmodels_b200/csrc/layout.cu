@@ -324,11 +324,29 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const PackDesc* __restr
   const int co0 = (blk.y / n_ci_blk) * kPackTile, ci0 = (blk.y % n_ci_blk) * kPackTile;
   const int row_len = kPackTile * nt, pitch = row_len + 1;
   const int valid_len = max(0, min(kPackTile, d.Cin - ci0)) * nt;  // contiguous floats per source row
-  for (int idx = threadIdx.x; idx < kPackTile * row_len; idx += blockDim.x) {
-    const int r = idx / row_len, k = idx - r * row_len;
-    const int co = co0 + r;
-    tile[r * pitch + k] =
-        (co < d.Cout && k < valid_len) ? d.src[(static_cast<long long>(co) * d.Cin + ci0) * nt + k] : 0.f;
+  // the 32 source rows of the tile are contiguous runs of 32 * ntaps floats: 16-byte loads (nine per thread for a
+  // 3x3 kernel, all independent) keep enough bytes in flight to stream at HBM rate; rows that are not 16-byte
+  // aligned or are cut by the channel count (stem, padded operands) take the scalar path
+  const bool vec4 = (row_len & 3) == 0 && valid_len == row_len && ((static_cast<long long>(d.Cin) * nt) & 3) == 0 &&
+                    ((reinterpret_cast<uintptr_t>(d.src) & 15) == 0);
+  if (vec4) {
+    const int row4 = row_len >> 2;
+    for (int idx = threadIdx.x; idx < kPackTile * row4; idx += blockDim.x) {
+      const int r = idx / row4, k = (idx - r * row4) * 4;
+      const int co = co0 + r;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (co < d.Cout)
+        v = __ldg(reinterpret_cast<const float4*>(d.src + (static_cast<long long>(co) * d.Cin + ci0) * nt + k));
+      float* t = tile + r * pitch + k;
+      t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < kPackTile * row_len; idx += blockDim.x) {
+      const int r = idx / row_len, k = idx - r * row_len;
+      const int co = co0 + r;
+      tile[r * pitch + k] =
+          (co < d.Cout && k < valid_len) ? d.src[(static_cast<long long>(co) * d.Cin + ci0) * nt + k] : 0.f;
+    }
   }
   __syncthreads();
   // work item = one 16-byte store: (row of the destination tile, tap, piece of 8 channels)
