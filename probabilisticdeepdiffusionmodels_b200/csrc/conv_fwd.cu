@@ -884,7 +884,8 @@ extern "C" int pddm_conv2d_fwd(const pddm_conv_params* p, pddm_stream_t stream_)
   a.m_tiles = a.tiles_w * a.tiles_h * tiles_b;
   a.block_n = pick_block_n(p->Cout);
   // small spatial extents: trade B-operand reuse for enough tiles to occupy every SM
-  while (a.block_n % 64 == 0 &&
+  const int min_bn = env_knobs().conv_min_bn > 0 ? env_knobs().conv_min_bn : 32;
+  while (a.block_n % 64 == 0 && a.block_n / 2 >= min_bn &&
          a.m_tiles * ((p->Cout + a.block_n / 2 - 1) / (a.block_n / 2)) <= launch_sms())
     a.block_n /= 2;
   a.n_tiles = (p->Cout + a.block_n - 1) / a.block_n;

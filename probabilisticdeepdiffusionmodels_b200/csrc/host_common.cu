@@ -29,6 +29,7 @@ const EnvKnobs& env_knobs() {
     k.gn_cc = env_int("PDDM_GN_CC");
     k.gn_ng = env_int("PDDM_GN_NG");
     k.attn_dbg = env_int("PDDM_ATTN_DBG");
+    k.conv_min_bn = env_int("PDDM_CONV_MIN_BN");
   });
   return k;
 }

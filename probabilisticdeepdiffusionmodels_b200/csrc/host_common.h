@@ -37,6 +37,7 @@ struct EnvKnobs {
   int gn_ng;            // PDDM_GN_NG=1: one compute group instead of two in the persistent GroupNorm kernels
   int gn_cc;            // PDDM_GN_CC: force the channel-chunk width of the persistent GroupNorm kernels
   int attn_dbg;         // PDDM_ATTN_DBG
+  int conv_min_bn;      // PDDM_CONV_MIN_BN: smallest channel tile the small-extent heuristic may pick (default 32)
 };
 const EnvKnobs& env_knobs();
 

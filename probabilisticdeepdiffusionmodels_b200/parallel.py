@@ -122,7 +122,7 @@ class OverlappedArenaAllReduce:
     full resolution | middle block, decoder, head].  ``plan.backward`` calls ``range_final`` as soon as every kernel
     that writes a tail range has been issued; the range is all-reduced on a high-priority communication stream (after
     the main and the weight-gradient streams' work issued so far) while the backward pass goes on.  ``hook(plan)``
-    after the backward pass reduces the head of the arena -- all that is still exposed, ~14 % of the bytes for the
+    after the backward pass reduces the head of the arena -- all that is still exposed, 10 % of the bytes for the
     CIFAR UNet -- and joins the streams.  1/W is folded into the fused Adam kernel (``optimizer.grad_scale``).
 
     Why the SM reserve: the GEMM kernels are persistent, one CTA per SM, each with a fixed share of the tiles.  NCCL's
