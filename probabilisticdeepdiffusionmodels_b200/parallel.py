@@ -190,6 +190,9 @@ class OverlappedArenaAllReduce:
     def __call__(self, plan):
         if not self._active():
             return
+        if not hasattr(plan, "grad_arena"):
+            raise TypeError("OverlappedArenaAllReduce needs the hand-scheduled step (plan.UNetPlan): this model takes "
+                            "the op-by-op path -- use FlatGradAllReduce / BucketedGradAllReduce")
         flat = plan.grad_arena
         head = flat.numel() if self._done_from is None else self._done_from
         self._done_from = None
