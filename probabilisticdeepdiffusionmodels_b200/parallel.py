@@ -162,6 +162,10 @@ class OverlappedArenaAllReduce:
     def attach(self, plan):
         """Have ``plan.backward`` report finished arena ranges to this object."""
         plan.comm = self if self._active() else None
+        self._done_from = None
+        if plan.comm is not None and plan.grad_arena.is_cuda:
+            from . import functional as F
+            F.set_sm_reserve(0)
         return self
 
     def range_final(self, plan, lo, hi):
@@ -169,6 +173,8 @@ class OverlappedArenaAllReduce:
         if not self._active() or hi <= lo:
             return
         flat = plan.grad_arena
+        if hi == flat.numel():
+            self._done_from = None  # first range of a step (also after a step that was abandoned half-way)
         if self._done_from is not None and hi != self._done_from:
             raise RuntimeError("OverlappedArenaAllReduce: ranges must arrive tail first and be contiguous")
         if flat.is_cuda:
