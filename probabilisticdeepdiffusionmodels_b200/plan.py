@@ -810,7 +810,11 @@ class PlanFunction(torch.autograd.Function):
         ctx.S = None
         if S is None:
             raise RuntimeError("PlanFunction: backward called twice (retain_graph is not supported on this path)")
-        plan.backward(S, dout.contiguous(), overlap=OVERLAP_EAGER[0])
+        comm, plan.comm = plan.comm, None  # the overlapped all-reduce belongs to the captured step, not to autograd
+        try:
+            plan.backward(S, dout.contiguous(), overlap=OVERLAP_EAGER[0])
+        finally:
+            plan.comm = comm
         flat = plan.grad_arena.clone()
         grads = []
         for prm in plan.params:
