@@ -464,13 +464,7 @@ def main():
         # rank leaves the loop after the same number of steps (a step contains collectives: ranks that replayed the
         # graph a different number of times would pair mismatched all-reduces)
         deadline = time.perf_counter() + 4.0
-        while True:
-            ready = torch.tensor([1 if (clk.proc is None or clk.rows or time.perf_counter() >= deadline) else 0],
-                                 dtype=torch.int32, device=dev)
-            if world > 1:
-                dist.all_reduce(ready, op=dist.ReduceOp.MIN)
-            if int(ready.item()):
-                break
+        while not parallel.all_ranks(clk.proc is None or bool(clk.rows) or time.perf_counter() >= deadline, dev):
             step(x_dev)
         barrier()
         clk.mark_start()

@@ -43,6 +43,17 @@ def shard_timesteps(diffusion_steps, rank, world):
     return list(range(2 + rank, diffusion_steps + 1, world))
 
 
+def all_ranks(flag, device=None, group=None):
+    """True iff ``flag`` is true on EVERY rank (one MIN all-reduce of an int32; a host sync).  Loops whose body
+    contains collectives -- a captured training step replayed "until something local happens" -- must leave on this,
+    not on the local condition: ranks that iterate a different number of times pair mismatched collectives."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return bool(flag)
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return bool(int(t.item()))
+
+
 def all_reduce_nll(parts, group=None):
     """Sum the ranks' partial NLL results with ONE all-reduce: ``parts`` = {"L_int", "L_0", "L_T": fp32 [B] per-sample
     vectors, "mse_sum": 0-dim float64 tensor, "mse_count": float}.  Returns the totals (same keys) on every rank."""

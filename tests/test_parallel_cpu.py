@@ -163,6 +163,35 @@ def _worker_arena(rank, world, port, out):
     dist.destroy_process_group()
 
 
+def _worker_all_ranks(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from probabilisticdeepdiffusionmodels_b200 import parallel
+    parallel.init_from_env("gloo")
+    assert parallel.all_ranks(True) is True
+    assert parallel.all_ranks(rank == 0) is False  # one rank not ready: nobody leaves
+    assert parallel.all_ranks(False) is False
+    # a loop with a collective in its body, left on all_ranks: every rank runs it the same number of times although
+    # the local condition turns true at different iterations
+    n, total = 0, torch.zeros(1)
+    while not parallel.all_ranks(n >= 2 + 3 * rank):
+        dist.all_reduce(total.add_(1.0))
+        n += 1
+    assert n == 2 + 3 * (world - 1)
+    if rank == 0:
+        torch.save({"ok": True, "n": n}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_loops_with_collectives_leave_together(tmp_path):
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_worker_all_ranks, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert torch.load(out)["ok"]
+    from probabilisticdeepdiffusionmodels_b200.parallel import all_ranks
+    assert all_ranks(True) is True and all_ranks(False) is False  # single process: the local flag
+
+
 def test_arena_grad_allreduce(tmp_path):
     out = str(tmp_path / "res.pt")
     mp.spawn(_worker_arena, args=(2, _free_port(), out), nprocs=2, join=True)
